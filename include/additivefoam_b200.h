@@ -1,0 +1,242 @@
+/*
+ * additivefoam_b200.h -- C ABI of the B200-native thermal hot path for AdditiveFOAM.
+ *
+ * This is the drop-in boundary.  Every entry point is plain C:
+ * opaque handles, plain pointers and sizes, `int` status (0 = ok, nonzero = error whose
+ * text is returned by b200_last_error()).  All pointers are HOST pointers unless the
+ * name ends in `_dev`.  Nothing here owns caller memory; outputs are caller-allocated.
+ *
+ * Reference interfaces replaced (paths relative to the AdditiveFOAM tree;
+ * SOLVER = applications/solvers/additiveFoam, MHS = SOLVER/movingHeatSource;
+ * [UPSTREAM] = OpenFOAM-10 source, not vendored in the reference):
+ *
+ *   b200_ldu_*            <- [UPSTREAM] Foam::lduMatrix::solver (PCG, PBiCGStab,
+ *                            diagonalSolver) + lduMatrix::preconditioner (DIC, DILU,
+ *                            diagonal), reached from SOLVER/thermo/TEqn.H:32-42 through
+ *                            fvMatrix<scalar>::solveSegregated; selected by
+ *                            tutorials/AMB2018-02-B/system/fvSolution:34-42.
+ *   b200_beam_qdot        <- MHS/heatSourceModels/heatSourceModel/heatSourceModel.H:194
+ *                            (virtual qDot()), body heatSourceModel.C:221-371.
+ *   b200_case_*           <- the per-time-step block of SOLVER/additiveFoam.C:66-95:
+ *                            updateProperties.H, setDeltaT.H, movingHeatSourceModel::update
+ *                            (MHS/movingHeatSourceModel/movingHeatSourceModel.C:100-150),
+ *                            solutionControls.H, thermo/TEqn.H (+thermoScheme.H,
+ *                            thermoSource.H).
+ *
+ * There is no CPU fallback behind this ABI: every call that computes needs a CUDA device.
+ */
+#ifndef ADDITIVEFOAM_B200_H
+#define ADDITIVEFOAM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ enums */
+
+/* lduMatrix::solver type ([UPSTREAM] symMatrix/asymMatrix tables; fvSolution `solver`). */
+enum { B200_SOLVER_PCG = 0, B200_SOLVER_PBICGSTAB = 1, B200_SOLVER_DIAGONAL = 2 };
+/* lduMatrix::preconditioner ([UPSTREAM]; fvSolution `preconditioner`). */
+enum { B200_PRECOND_NONE = 0, B200_PRECOND_DIAGONAL = 1, B200_PRECOND_DIC = 2, B200_PRECOND_DILU = 3 };
+/* fvPatchField types on T (tutorials/AMB2018-02-B/0/T:21-41; multiLayerPBF/0/T:23-40). */
+enum { B200_BC_ZERO_GRADIENT = 0, B200_BC_FIXED_VALUE = 1, B200_BC_MIXED_TEMPERATURE = 2 };
+/* Sides of a blockMesh hex block in blockMesh's own boundary order [UPSTREAM block::createBoundary]. */
+enum { B200_XMIN = 0, B200_XMAX = 1, B200_YMIN = 2, B200_YMAX = 3, B200_ZMIN = 4, B200_ZMAX = 5 };
+/* heatSourceModel run-time types (MHS/heatSourceModels/...). */
+enum { B200_SUPER_GAUSSIAN = 0, B200_MODIFIED_SUPER_GAUSSIAN = 1, B200_PROJECTED_GAUSSIAN = 2 };
+/* absorptionModel run-time types (MHS/absorptionModels/...). */
+enum { B200_ABSORPTION_CONSTANT = 0, B200_ABSORPTION_KELLY = 1 };
+enum { B200_KELLY_CONE = 0, B200_KELLY_CYLINDER = 1 };
+/* Fields that b200_case_get_field / set_field can address. */
+enum {
+    B200_FIELD_T = 0, B200_FIELD_ALPHA_SOLID = 1, B200_FIELD_ALPHA_POWDER = 2,
+    B200_FIELD_KAPPA = 3, B200_FIELD_CP = 4, B200_FIELD_QDOT = 5,
+    B200_FIELD_DFDT = 6, B200_FIELD_T0 = 7
+};
+
+/* ------------------------------------------------------- case description */
+
+/* One hex block, uniform grading: tutorials/AMB2018-02-B/system/blockMeshDict:16-38.
+ * Cell index = i + nx*(j + ny*k); internal faces in upper-triangular order. */
+typedef struct b200_block_mesh {
+    int32_t nx, ny, nz;
+    double  min[3];
+    double  max[3];
+} b200_block_mesh;
+
+/* One boundary patch of T.  kappa, Cp, alpha.* are zeroGradient on every patch
+ * (SOLVER/createFields.H:16-44,84-110). */
+typedef struct b200_patch {
+    int32_t type;        /* B200_BC_* */
+    int32_t nSides;      /* block sides making up the patch, in blockMeshDict order */
+    int32_t sides[6];
+    double  value;       /* fixedValue */
+    double  h;           /* mixedTemperature: mixedTemperatureFvPatchScalarField.C:157-188 */
+    double  emissivity;
+    double  Tinf;
+} b200_patch;
+
+/* constant/transportProperties (SOLVER/readTransportProperties.H:13-73) and
+ * constant/thermoPath (SOLVER/createFields.H:46-71). */
+typedef struct b200_material {
+    double  kappa[3][3]; /* [solid, liquid, powder][c0, c1, c2] Polynomial<3> */
+    double  Cp[3][3];
+    double  rho;
+    double  Lf;
+    int32_t nThermo;     /* rows of thermoPath */
+    const double* thermoT;      /* x column: temperature */
+    const double* thermoAlpha;  /* y column: solid fraction */
+} b200_material;
+
+/* One entry of constant/heatSourceDict `sources` (tutorials/AMB2018-02-B/constant/heatSourceDict:18-46). */
+typedef struct b200_beam {
+    int32_t heatSourceModel;   /* B200_SUPER_GAUSSIAN ... */
+    double  dimensions[3];
+    int32_t nPoints[3];
+    int32_t transient;         /* heatSourceModel.C:104-118 */
+    double  isoValue;
+    double  k, m, A, B;        /* shape coefficients */
+    int32_t absorptionModel;   /* B200_ABSORPTION_* */
+    double  eta;               /* constant */
+    int32_t kellyGeometry;     /* B200_KELLY_* */
+    double  eta0, etaMin;
+    double  deltaT;            /* beam sub-cycle step, <=0 means GREAT (movingBeam.C:58,62) */
+    int32_t hitPathIntervals;  /* movingBeam.C:63 */
+    int32_t nSegments;         /* data lines of the scan path file (header excluded) */
+    const double* path;        /* nSegments x 6: mode x y z power parameter (segment.C:64-75) */
+} b200_beam;
+
+/* system/controlDict + system/fvSolution entries used by the path. */
+typedef struct b200_controls {
+    double  startTime, endTime, deltaT;
+    int32_t adjustTimeStep;
+    double  maxCo, maxDi, maxAlphaCo, maxDeltaT;
+    double  writeInterval;     /* adjustableRunTime write interval; <=0 disables write-time snapping */
+    int32_t nThermoCorrectors; /* SOLVER/solutionControls.H:2-12 */
+    double  thermoTolerance;
+    double  Tmax;              /* <=0 means vGreat */
+    int32_t explicitSolve;     /* SOLVER/solutionControls.H:31-49 */
+    int32_t solver;            /* B200_SOLVER_PCG | B200_SOLVER_PBICGSTAB */
+    int32_t preconditioner;    /* B200_PRECOND_* */
+    double  tolerance, relTol;
+    int32_t minIter, maxIter;
+} b200_controls;
+
+typedef struct b200_case_desc {
+    b200_block_mesh mesh;
+    int32_t nPatches;
+    const b200_patch* patches;
+    b200_material material;
+    int32_t nBeams;
+    const b200_beam* beams;
+    b200_controls controls;
+    double  Tinitial;          /* 0/T internalField uniform */
+    double  powderZMin;        /* alpha.powder = 1 for cell centres with z > powderZMin; use +1e300 for none */
+} b200_case_desc;
+
+/* What one time step reports (the reference prints these: setDeltaT.H:15,33,50;
+ * solutionControls.H:18; TEqn.H:55-56; [UPSTREAM] solver performance line). */
+typedef struct b200_step_report {
+    double  time, deltaT;
+    double  alphaCoNum, DiNum;
+    double  totalPower;
+    int32_t explicitStep;      /* 1 when the diagonal (explicit) form was used */
+    int32_t nThermoCorr;       /* corrector passes executed */
+    double  thermoResidual;    /* last max|alpha1 - alpha10| */
+    int32_t nSolveIterations;  /* Krylov iterations summed over correctors */
+    int32_t lastSolveIterations;
+    double  lastInitialResidual, lastFinalResidual;
+} b200_step_report;
+
+typedef struct b200_solver_perf {
+    double  initialResidual, finalResidual;
+    int32_t nIterations, converged, singular;
+} b200_solver_perf;
+
+/* ------------------------------------------------------------ the calls */
+
+typedef struct b200_ctx  b200_ctx;
+typedef struct b200_ldu  b200_ldu;
+typedef struct b200_case b200_case;
+
+const char* b200_last_error(void);
+/* ABI version, bumped on any incompatible change. */
+int  b200_abi_version(void);
+
+/* One context per process = one GPU = one subdomain (the reference's one MPI rank).
+ * nccl_unique_id: 128-byte ncclUniqueId shared by all ranks, or NULL when nranks == 1. */
+int  b200_nccl_unique_id(void* out128);
+int  b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, int nranks, b200_ctx** out);
+int  b200_ctx_destroy(b200_ctx* ctx);
+int  b200_ctx_synchronize(b200_ctx* ctx);
+
+/* ---- B1: lduMatrix::solver.  Addressing is cached in the handle; coefficients are per call.
+ * lower/upper: [UPSTREAM] lduAddressing::lowerAddr()/upperAddr() (upper-triangular order).
+ * Interfaces are processor patches: faceCells per interface, neighbour rank per interface. */
+int  b200_ldu_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces,
+                     const int32_t* lower, const int32_t* upper,
+                     int32_t nInterfaces, const int32_t* ifaceNeighbRank, const int32_t* ifaceSize,
+                     const int32_t* const* ifaceFaceCells, b200_ldu** out);
+int  b200_ldu_destroy(b200_ldu* ldu);
+/* Declare that the addressing is a single blockMesh hex block (verified bit-exactly against
+ * lower/upper); enables the structured kernels.  Returns nonzero if it does not match. */
+int  b200_ldu_set_block(b200_ldu* ldu, int32_t nx, int32_t ny, int32_t nz);
+/* [UPSTREAM] lduMatrix::solver::solve(psi, source).  lower == NULL means symmetric
+ * (lower aliases upper).  psi is in/out. */
+int  b200_ldu_solve(b200_ldu* ldu, int32_t solver, int32_t preconditioner,
+                    const double* diag, const double* upper, const double* lower,
+                    const double* const* ifaceBouCoeffs,
+                    const double* source, double* psi,
+                    double tolerance, double relTol, int32_t minIter, int32_t maxIter,
+                    b200_solver_perf* perf);
+/* Same with device-resident arrays (no copies); used by the resident stepper and the benchmark. */
+int  b200_ldu_solve_dev(b200_ldu* ldu, int32_t solver, int32_t preconditioner,
+                        const double* diag_dev, const double* upper_dev, const double* lower_dev,
+                        const double* const* ifaceBouCoeffs_dev,
+                        const double* source_dev, double* psi_dev,
+                        double tolerance, double relTol, int32_t minIter, int32_t maxIter,
+                        b200_solver_perf* perf);
+/* [UPSTREAM] lduMatrix::Amul on its own (the "Amul HBM GB/s" micro-benchmark and parity probe). */
+int  b200_ldu_amul(b200_ldu* ldu, const double* diag, const double* upper, const double* lower,
+                   const double* const* ifaceBouCoeffs, const double* psi, double* Apsi);
+int  b200_ldu_amul_dev(b200_ldu* ldu, const double* diag_dev, const double* upper_dev,
+                       const double* lower_dev, const double* const* ifaceBouCoeffs_dev,
+                       const double* psi_dev, double* Apsi_dev);
+/* One application of the preconditioner, wA = M^-1 rA (factor computed from the given matrix). */
+int  b200_ldu_precondition(b200_ldu* ldu, int32_t preconditioner,
+                           const double* diag, const double* upper, const double* lower,
+                           const double* rA, double* wA);
+/* Level schedule of the cached addressing (renumbering parity probe): level of each cell. */
+int  b200_ldu_levels(b200_ldu* ldu, int32_t* levelOfCell, int32_t* nLevels);
+
+/* ---- B2: heatSourceModel::qDot() for one beam state on a block mesh.
+ * Writes qDot (W/m^3) for all cells (host array, mesh.nx*ny*nz) and the Riemann sum of V*w. */
+int  b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam* beam,
+                    const double position[3], const double dimensions[3], double power,
+                    double* qDot, double* sumWeights, double* volumeUsed, double* absorbedPower);
+
+/* ---- The GPU-resident thermal step (everything in SURVEY section 3.2 items 1,3,4,6,8). */
+int  b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out);
+int  b200_case_destroy(b200_case* c);
+/* 1 while the reference's `runTime.run()` would be true. */
+int  b200_case_running(b200_case* c);
+int  b200_case_step(b200_case* c, b200_step_report* report);
+/* Fixed-dt stepping for throughput runs: same step, adjustTimeStep bypassed. */
+int  b200_case_n_cells(b200_case* c, int64_t* nLocal, int64_t* nGlobal);
+int  b200_case_get_field(b200_case* c, int32_t field, double* out);
+int  b200_case_set_field(b200_case* c, int32_t field, const double* in);
+/* Device time (ms) spent in the kernels of the last step by group, for the benchmark:
+ * [0] properties+dt numbers, [1] heat source, [2] assembly, [3] corrector fold+alpha update,
+ * [4] Krylov solve. */
+int  b200_case_kernel_launches(b200_case* c, int64_t* launches);
+
+/* Scan path text -> nSegments x 6 table (MHS/movingBeam/movingBeam.C:89-148: header line
+ * skipped, blank lines skipped).  Returns the number of segments, or -1. */
+int  b200_scan_path_parse(const char* text, double* out, int32_t maxSegments);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADDITIVEFOAM_B200_H */

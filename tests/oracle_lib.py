@@ -1,0 +1,125 @@
+"""ctypes binding of the CPU oracle (oracle/libaf_oracle.so).  TEST INFRASTRUCTURE ONLY."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+from additivefoam_b200 import abi, cases
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(ROOT, "oracle", "libaf_oracle.so")
+
+dp = abi.c_double_p
+ip = abi.c_int32_p
+
+
+def _ensure_built():
+    srcs = [os.path.join(ROOT, "oracle", f) for f in ("af_oracle_capi.cpp", "af_thermal.hpp", "af_beam.hpp", "af_ldu.hpp")]
+    srcs.append(os.path.join(ROOT, "include", "additivefoam_b200.h"))
+    if (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs if os.path.exists(s)):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+
+
+def load():
+    _ensure_built()
+    L = C.CDLL(_SO)
+    L.afo_case_create.restype = C.c_void_p
+    L.afo_case_create.argtypes = [C.POINTER(abi.CaseDesc), C.c_int]
+    L.afo_case_destroy.argtypes = [C.c_void_p]
+    L.afo_case_running.argtypes = [C.c_void_p]
+    L.afo_case_step.argtypes = [C.c_void_p, C.POINTER(abi.StepReport)]
+    L.afo_case_n_cells.restype = C.c_int64
+    L.afo_case_n_cells.argtypes = [C.c_void_p]
+    L.afo_case_get_field.argtypes = [C.c_void_p, C.c_int, dp]
+    L.afo_case_set_field.argtypes = [C.c_void_p, C.c_int, dp]
+    L.afo_case_residual_log.argtypes = [C.c_void_p, dp, C.c_int32]
+    L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+    for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
+        getattr(L, f).restype = C.c_double
+        getattr(L, f).argtypes = [C.c_void_p]
+    L.afo_absorption_eta.restype = C.c_double
+    L.afo_absorption_eta.argtypes = [C.POINTER(abi.Beam), C.c_double]
+    L.afo_shape_V0.restype = C.c_double
+    L.afo_shape_V0.argtypes = [C.POINTER(abi.Beam), dp]
+    L.afo_shape_weight.restype = C.c_double
+    L.afo_shape_weight.argtypes = [C.POINTER(abi.Beam), dp, dp]
+    L.afo_interpolateXY.restype = C.c_double
+    L.afo_interpolateXY.argtypes = [C.c_double, C.c_int32, dp, dp]
+    L.afo_beam_adjust_deltaT.restype = C.c_double
+    L.afo_beam_adjust_deltaT.argtypes = [C.POINTER(abi.Beam), C.c_double, C.c_double, C.c_double, C.c_double, C.c_double]
+    L.afo_beam_move.argtypes = [C.POINTER(abi.Beam), C.c_double, C.c_double, C.c_int32, dp, dp, dp, ip, dp]
+    L.afo_beam_qdot.argtypes = [C.POINTER(abi.BlockMesh), C.POINTER(abi.Beam), dp, dp, C.c_double, dp, dp, dp, dp]
+    L.afo_scan_path_parse.argtypes = [C.c_char_p, dp, C.c_int32]
+    L.afo_block_addressing.argtypes = [C.POINTER(abi.BlockMesh), C.c_int, C.c_int, ip, ip, ip, ip]
+    L.afo_ldu_amul.argtypes = [C.c_int32, C.c_int32, ip, ip, dp, dp, dp, dp, dp]
+    L.afo_ldu_precondition.argtypes = [C.c_int32, C.c_int32, ip, ip, dp, dp, dp, C.c_int, dp, dp, dp]
+    L.afo_ldu_solve.argtypes = [C.c_int32, C.c_int32, ip, ip, dp, dp, dp, dp, dp, C.c_int, C.c_int, C.c_double,
+                                C.c_double, C.c_int32, C.c_int32, C.POINTER(abi.SolverPerf), dp, C.c_int32, ip]
+    L.afo_ldu_levels.argtypes = [C.c_int32, C.c_int32, ip, ip, ip, ip]
+    return L
+
+
+def P(a):
+    """numpy array -> typed pointer (None passes NULL)."""
+    if a is None:
+        return None
+    if a.dtype == np.float64:
+        return a.ctypes.data_as(dp)
+    if a.dtype == np.int32:
+        return a.ctypes.data_as(ip)
+    raise TypeError(a.dtype)
+
+
+class OracleCase:
+    def __init__(self, case, ranks=1, lib=None):
+        self.L = lib or load()
+        self.built = cases.BuiltCase(case)
+        self.h = self.L.afo_case_create(C.byref(self.built.desc), ranks)
+        assert self.h, "oracle case creation failed"
+        self.n = self.L.afo_case_n_cells(self.h)
+
+    def running(self):
+        return bool(self.L.afo_case_running(self.h))
+
+    def step(self):
+        rep = abi.StepReport()
+        self.L.afo_case_step(self.h, C.byref(rep))
+        return rep
+
+    def field(self, f):
+        out = np.empty(self.n, dtype=np.float64)
+        assert self.L.afo_case_get_field(self.h, f, P(out)) == 0
+        return out
+
+    def set_field(self, f, a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        assert self.L.afo_case_set_field(self.h, f, P(a)) == 0
+
+    def residual_log(self):
+        out = np.empty(4096)
+        n = self.L.afo_case_residual_log(self.h, P(out), 4096)
+        return out[:n].copy()
+
+    def close(self):
+        if self.h:
+            self.L.afo_case_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def block_addressing(L, n, r=0, R=1):
+    bm = abi.BlockMesh()
+    bm.nx, bm.ny, bm.nz = n
+    for q in range(3):
+        bm.min[q], bm.max[q] = 0.0, float(n[q])
+    nc, nf = C.c_int32(), C.c_int32()
+    L.afo_block_addressing(C.byref(bm), r, R, C.byref(nc), C.byref(nf), None, None)
+    lo = np.empty(nf.value, dtype=np.int32)
+    up = np.empty(nf.value, dtype=np.int32)
+    L.afo_block_addressing(C.byref(bm), r, R, C.byref(nc), C.byref(nf), P(lo), P(up))
+    return nc.value, nf.value, lo, up
