@@ -1,0 +1,282 @@
+// extern "C" surface declared in include/additivefoam_b200.h.  Exceptions stop here.
+#include "../../include/additivefoam_b200.h"
+#include "ctx.cuh"
+#include "ldu.cuh"
+#include "thermal.cuh"
+#include <cstring>
+#include <sstream>
+
+using namespace b200;
+
+struct b200_ctx { Ctx* p; };
+struct b200_ldu { Ldu* p; };
+struct b200_case { ThermalCase* p; };
+
+static thread_local std::string g_err;
+
+#define B200_TRY try {
+#define B200_CATCH                                                                               \
+    }                                                                                            \
+    catch (const std::exception& e) { g_err = e.what(); return 1; }                              \
+    catch (...) { g_err = "unknown error"; return 1; }                                           \
+    return 0;
+
+extern "C" {
+
+const char* b200_last_error(void) { return g_err.c_str(); }
+int b200_abi_version(void) { return 1; }
+
+int b200_nccl_unique_id(void* out128)
+{
+    B200_TRY
+    ncclUniqueId id;
+    B200_NCCL(ncclGetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    std::memcpy(out128, &id, sizeof(id));
+    B200_CATCH
+}
+
+int b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, int nranks, b200_ctx** out)
+{
+    B200_TRY
+    *out = new b200_ctx{new Ctx(device_ordinal, nccl_unique_id, rank, nranks)};
+    B200_CATCH
+}
+int b200_ctx_destroy(b200_ctx* ctx)
+{
+    B200_TRY
+    if (ctx) { delete ctx->p; delete ctx; }
+    B200_CATCH
+}
+int b200_ctx_synchronize(b200_ctx* ctx)
+{
+    B200_TRY
+    ctx->p->sync();
+    B200_CATCH
+}
+
+int b200_ldu_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper, int32_t nInterfaces,
+                    const int32_t* ifaceNeighbRank, const int32_t* ifaceSize, const int32_t* const* ifaceFaceCells, b200_ldu** out)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    *out = new b200_ldu{new Ldu(ctx->p, nCells, nFaces, lower, upper, nInterfaces, ifaceNeighbRank, ifaceSize, ifaceFaceCells)};
+    B200_CATCH
+}
+int b200_ldu_destroy(b200_ldu* ldu)
+{
+    B200_TRY
+    if (ldu) { delete ldu->p; delete ldu; }
+    B200_CATCH
+}
+int b200_ldu_set_block(b200_ldu* ldu, int32_t nx, int32_t ny, int32_t nz)
+{
+    B200_TRY
+    ldu->p->setBlock(nx, ny, nz);
+    B200_CATCH
+}
+
+// stage host arrays on the device (buffers cached in the handle)
+static double* stage_in(Ldu& L, int slot, const double* host, size_t n)
+{
+    if (!host) return nullptr;
+    if (!L.stage[slot]) {
+        const size_t cap = std::max<size_t>((size_t)L.nFaces, (size_t)L.nCells) + 2 * (size_t)L.nCells + 16;
+        L.stage[slot] = dev_alloc<double>(cap);
+    }
+    h2d(L.stage[slot], host, n, L.ctx->stream);
+    return L.stage[slot];
+}
+static std::vector<const double*> stage_bou(Ldu& L, const double* const* hostBou)
+{
+    std::vector<const double*> out;
+    if (L.ifaces.empty() || !hostBou) return out;
+    if (L.stageBou.empty())
+        for (auto& it : L.ifaces) L.stageBou.push_back(dev_alloc<double>(it.size));
+    for (size_t p = 0; p < L.ifaces.size(); p++) {
+        h2d(L.stageBou[p], hostBou[p], L.ifaces[p].size, L.ctx->stream);
+        out.push_back(L.stageBou[p]);
+    }
+    return out;
+}
+
+int b200_ldu_solve_dev(b200_ldu* ldu, int32_t solver, int32_t preconditioner, const double* diag_dev, const double* upper_dev,
+                       const double* lower_dev, const double* const* ifaceBouCoeffs_dev, const double* source_dev, double* psi_dev,
+                       double tolerance, double relTol, int32_t minIter, int32_t maxIter, b200_solver_perf* perf)
+{
+    B200_TRY
+    Ldu& L = *ldu->p;
+    B200_CUDA(cudaSetDevice(L.ctx->device));
+    MatrixView A; A.diag = diag_dev; A.upper = upper_dev; A.lower = lower_dev ? lower_dev : upper_dev; A.bouCoeffs = ifaceBouCoeffs_dev;
+    SolveControls sc; sc.solver = solver; sc.precond = preconditioner; sc.tolerance = tolerance; sc.relTol = relTol;
+    sc.minIter = minIter; sc.maxIter = maxIter;
+    const SolvePerf sp = L.solve(A, source_dev, psi_dev, sc);
+    L.ctx->sync();
+    if (perf) {
+        perf->initialResidual = sp.initialResidual; perf->finalResidual = sp.finalResidual;
+        perf->nIterations = sp.nIterations; perf->converged = sp.converged; perf->singular = sp.singular;
+    }
+    B200_CATCH
+}
+
+int b200_ldu_solve(b200_ldu* ldu, int32_t solver, int32_t preconditioner, const double* diag, const double* upper, const double* lower,
+                   const double* const* ifaceBouCoeffs, const double* source, double* psi, double tolerance, double relTol,
+                   int32_t minIter, int32_t maxIter, b200_solver_perf* perf)
+{
+    B200_TRY
+    Ldu& L = *ldu->p;
+    B200_CUDA(cudaSetDevice(L.ctx->device));
+    const double* d = stage_in(L, 0, diag, L.nCells);
+    const double* u = stage_in(L, 1, upper, L.nFaces);
+    const double* l = stage_in(L, 2, lower, L.nFaces);
+    const double* b = stage_in(L, 3, source, L.nCells);
+    double* x = stage_in(L, 4, psi, L.nCells);
+    std::vector<const double*> bou = stage_bou(L, ifaceBouCoeffs);
+    MatrixView A; A.diag = d; A.upper = u; A.lower = l ? l : u; A.bouCoeffs = bou.empty() ? nullptr : bou.data();
+    SolveControls sc; sc.solver = solver; sc.precond = preconditioner; sc.tolerance = tolerance; sc.relTol = relTol;
+    sc.minIter = minIter; sc.maxIter = maxIter;
+    const SolvePerf sp = L.solve(A, b, x, sc);
+    d2h(psi, x, L.nCells, L.ctx->stream);
+    L.ctx->sync();
+    if (perf) {
+        perf->initialResidual = sp.initialResidual; perf->finalResidual = sp.finalResidual;
+        perf->nIterations = sp.nIterations; perf->converged = sp.converged; perf->singular = sp.singular;
+    }
+    B200_CATCH
+}
+
+int b200_ldu_amul_dev(b200_ldu* ldu, const double* diag_dev, const double* upper_dev, const double* lower_dev,
+                      const double* const* ifaceBouCoeffs_dev, const double* psi_dev, double* Apsi_dev)
+{
+    B200_TRY
+    Ldu& L = *ldu->p;
+    MatrixView A; A.diag = diag_dev; A.upper = upper_dev; A.lower = lower_dev ? lower_dev : upper_dev; A.bouCoeffs = ifaceBouCoeffs_dev;
+    L.amul(A, psi_dev, Apsi_dev);
+    B200_CATCH
+}
+
+int b200_ldu_amul(b200_ldu* ldu, const double* diag, const double* upper, const double* lower, const double* const* ifaceBouCoeffs,
+                  const double* psi, double* Apsi)
+{
+    B200_TRY
+    Ldu& L = *ldu->p;
+    B200_CUDA(cudaSetDevice(L.ctx->device));
+    const double* d = stage_in(L, 0, diag, L.nCells);
+    const double* u = stage_in(L, 1, upper, L.nFaces);
+    const double* l = stage_in(L, 2, lower, L.nFaces);
+    // psi sits in the middle of its staging buffer so that block kernels may touch one plane either side
+    if (!L.stage[4]) L.stage[4] = dev_alloc<double>((size_t)3 * L.nCells + 16);
+    double* x = L.stage[4] + L.nCells;
+    h2d(x, psi, L.nCells, L.ctx->stream);
+    double* y = stage_in(L, 5, psi, L.nCells);
+    std::vector<const double*> bou = stage_bou(L, ifaceBouCoeffs);
+    MatrixView A; A.diag = d; A.upper = u; A.lower = l ? l : u; A.bouCoeffs = bou.empty() ? nullptr : bou.data();
+    L.amul(A, x, y);
+    d2h(Apsi, y, L.nCells, L.ctx->stream);
+    L.ctx->sync();
+    B200_CATCH
+}
+
+int b200_ldu_precondition(b200_ldu* ldu, int32_t preconditioner, const double* diag, const double* upper, const double* lower,
+                          const double* rA, double* wA)
+{
+    B200_TRY
+    Ldu& L = *ldu->p;
+    B200_CUDA(cudaSetDevice(L.ctx->device));
+    const double* d = stage_in(L, 0, diag, L.nCells);
+    const double* u = stage_in(L, 1, upper, L.nFaces);
+    const double* l = stage_in(L, 2, lower, L.nFaces);
+    const double* r = stage_in(L, 3, rA, L.nCells);
+    if (!L.stage[6]) L.stage[6] = dev_alloc<double>((size_t)3 * L.nCells + 16);
+    double* w = L.stage[6] + L.nCells;
+    MatrixView A; A.diag = d; A.upper = u; A.lower = l ? l : u;
+    L.precondition(preconditioner, A, r, w);
+    d2h(wA, w, L.nCells, L.ctx->stream);
+    L.ctx->sync();
+    B200_CATCH
+}
+
+int b200_ldu_levels(b200_ldu* ldu, int32_t* levelOfCell, int32_t* nLevels)
+{
+    B200_TRY
+    ldu->p->levels(levelOfCell, nLevels);
+    B200_CATCH
+}
+
+int b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam* beam, const double position[3],
+                   const double dimensions[3], double power, double* qDot, double* sumWeights, double* volumeUsed,
+                   double* absorbedPower)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    beam_qdot_standalone(ctx->p, *mesh, *beam, position, dimensions, power, qDot, sumWeights, volumeUsed, absorbedPower);
+    B200_CATCH
+}
+
+int b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    *out = new b200_case{new ThermalCase(ctx->p, *desc)};
+    B200_CATCH
+}
+int b200_case_destroy(b200_case* c)
+{
+    B200_TRY
+    if (c) { delete c->p; delete c; }
+    B200_CATCH
+}
+int b200_case_running(b200_case* c) { return c->p->running() ? 1 : 0; }
+int b200_case_step(b200_case* c, b200_step_report* report)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->step(report);
+    B200_CATCH
+}
+int b200_case_n_cells(b200_case* c, int64_t* nLocal, int64_t* nGlobal)
+{
+    B200_TRY
+    if (nLocal) *nLocal = c->p->nLocal();
+    if (nGlobal) *nGlobal = c->p->nGlobal();
+    B200_CATCH
+}
+int b200_case_get_field(b200_case* c, int32_t field, double* out)
+{
+    B200_TRY
+    c->p->getField(field, out);
+    B200_CATCH
+}
+int b200_case_set_field(b200_case* c, int32_t field, const double* in)
+{
+    B200_TRY
+    c->p->setField(field, in);
+    B200_CATCH
+}
+int b200_case_kernel_launches(b200_case*, int64_t* launches)
+{
+    *launches = g_launches;
+    return 0;
+}
+
+int b200_scan_path_parse(const char* text, double* out, int32_t maxSegments)
+{
+    // MHS/movingBeam/movingBeam.C:89-148: first line is a header, blank lines are skipped,
+    // each data line is "mode x y z power parameter" (segment.C:64-75)
+    std::istringstream is(text ? text : "");
+    std::string line;
+    if (!std::getline(is, line)) return 0;
+    int n = 0;
+    while (std::getline(is, line)) {
+        if (line.empty()) continue;
+        std::stringstream ls(line);
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        ls >> v[0] >> v[1] >> v[2] >> v[3] >> v[4] >> v[5];
+        if (n >= maxSegments) return -1;
+        for (int q = 0; q < 6; q++) out[6 * n + q] = v[q];
+        n++;
+    }
+    return n;
+}
+
+} // extern "C"

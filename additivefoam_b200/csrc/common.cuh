@@ -1,0 +1,124 @@
+// Shared helpers for the sm_100a kernels: error handling, launch counting, deterministic
+// block reductions.  All arithmetic is FP64 and compiled with -fmad=false so that a
+// product followed by a sum rounds twice, exactly as the reference's x86-64 build does.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <stdexcept>
+
+namespace b200 {
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define B200_CUDA(expr)                                                                         \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            throw ::b200::Error(std::string(#expr) + ": " + cudaGetErrorString(e_) + " at " +   \
+                                __FILE__ + ":" + std::to_string(__LINE__));                     \
+    } while (0)
+
+#define B200_CHECK(cond, msg)                                                                   \
+    do {                                                                                        \
+        if (!(cond)) throw ::b200::Error(std::string(msg) + " (" #cond ") at " + __FILE__ + ":" + \
+                                         std::to_string(__LINE__));                             \
+    } while (0)
+
+extern int64_t g_launches;     // kernels launched by this library (bench.py "gpu_launches")
+inline void count_launch(int n = 1) { g_launches += n; }
+#define B200_LAUNCH_CHECK() do { ::b200::count_launch(); B200_CUDA(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------------------------------
+// Deterministic reductions.  Every reducing kernel runs with a fixed grid; each block
+// reduces with a fixed shuffle tree, writes its partial to `partials[slot][block]`, and
+// the last block to finish (atomic ticket) sums the partials in a fixed order.  The result
+// therefore depends only on (grid, block) geometry, never on scheduling.
+// ---------------------------------------------------------------------------------------
+constexpr int RED_THREADS = 256;
+constexpr int RED_MAX_BLOCKS = 2048;     // partials per slot
+
+struct Sum { __device__ static double id() { return 0.0; } __device__ static double op(double a, double b) { return a + b; } };
+struct Max { __device__ static double id() { return -1e300; } __device__ static double op(double a, double b) { return a > b ? a : b; } };
+struct Min { __device__ static double id() { return 1e300; } __device__ static double op(double a, double b) { return a < b ? a : b; } };
+
+template <class Op> __device__ inline double warp_reduce(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = Op::op(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Reduce `v` over the block (any block size that is a multiple of 32, <= 1024); result valid in thread 0.
+template <class Op> __device__ inline double block_reduce(double v, double* smem /* >= 32 doubles */)
+{
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int lane = tid & 31, warp = tid >> 5;
+    v = warp_reduce<Op>(v);
+    __syncthreads();
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (nthreads + 31) >> 5;
+        v = lane < nw ? smem[lane] : Op::id();
+        v = warp_reduce<Op>(v);
+    }
+    return v;
+}
+
+struct RedWork {
+    double* partials;      // [nSlots][RED_MAX_BLOCKS]
+    unsigned* ticket;      // one counter per reducing kernel in flight (serialised on one stream)
+    double* result;        // [nSlots] final values
+};
+
+// Called by every thread of every block after computing its private values v[0..N).
+// ops[i]: 0 sum, 1 max, 2 min.  Writes result[slot0 + i].
+template <int N>
+__device__ inline void grid_reduce(double (&v)[N], const int (&ops)[N], RedWork w, int slot0, double* smem)
+{
+    const int tid = threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z);
+    const int nthreads = blockDim.x * blockDim.y * blockDim.z;
+    const int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    const int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    __shared__ bool isLast;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        double r = ops[i] == 0 ? block_reduce<Sum>(v[i], smem) : ops[i] == 1 ? block_reduce<Max>(v[i], smem) : block_reduce<Min>(v[i], smem);
+        if (tid == 0) w.partials[(size_t)(slot0 + i) * RED_MAX_BLOCKS + bid] = r;
+    }
+    __threadfence();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(w.ticket, 1u);
+        isLast = (t == (unsigned)nblocks - 1u);
+    }
+    __syncthreads();
+    if (!isLast) return;
+    __threadfence();
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const double* p = w.partials + (size_t)(slot0 + i) * RED_MAX_BLOCKS;
+        double acc = ops[i] == 0 ? 0.0 : ops[i] == 1 ? -1e300 : 1e300;
+        for (int b = tid; b < nblocks; b += nthreads) {
+            const double x = __ldcg(p + b);
+            acc = ops[i] == 0 ? acc + x : ops[i] == 1 ? (acc > x ? acc : x) : (acc < x ? acc : x);
+        }
+        double r = ops[i] == 0 ? block_reduce<Sum>(acc, smem) : ops[i] == 1 ? block_reduce<Max>(acc, smem) : block_reduce<Min>(acc, smem);
+        if (tid == 0) w.result[slot0 + i] = r;
+    }
+    if (tid == 0) *w.ticket = 0u;
+}
+
+inline int red_blocks_for(int64_t n, int threads = RED_THREADS)
+{
+    int64_t b = (n + threads - 1) / threads;
+    if (b > RED_MAX_BLOCKS) b = RED_MAX_BLOCKS;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+} // namespace b200

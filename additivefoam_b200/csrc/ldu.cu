@@ -1,0 +1,421 @@
+#include "ldu_kernels.cuh"
+#include "ctx.cuh"
+#include <algorithm>
+#include <cstring>
+
+namespace b200 {
+
+// ------------------------------------------------------------------ cooperative launch helper
+template <class K> static int coop_max_blocks(Ctx* ctx, K kernel)
+{
+    int perSm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, BLK, 0));
+    B200_CHECK(perSm > 0, "sweep kernel does not fit on an SM");
+    return perSm * ctx->smCount;
+}
+template <class K, class... Args> static void coop_launch(Ctx* ctx, K kernel, int64_t maxWork, Args... args)
+{
+    int grid = coop_max_blocks(ctx, kernel);
+    const int64_t want = (maxWork + BLK - 1) / BLK;
+    if (want < grid) grid = (int)std::max<int64_t>(want, 1);
+    void* ptrs[] = {(void*)&args...};
+    B200_CUDA(cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(BLK), ptrs, 0, ctx->stream));
+    count_launch();
+}
+
+// ------------------------------------------------------------------ construction
+Ldu::Ldu(Ctx* c, int nCells_, int nFaces_, const int* lower, const int* upper, int nInterfaces, const int* ifaceNeighbRank,
+         const int* ifaceSize, const int* const* ifaceFaceCells)
+    : ctx(c), nCells(nCells_), nFaces(nFaces_)
+{
+    B200_CHECK(nCells >= 0 && nFaces >= 0, "negative sizes");
+    hasGeneral = true;
+    h_lower.assign(lower, lower + nFaces);
+    h_upper.assign(upper, upper + nFaces);
+    for (int f = 0; f < nFaces; f++) {
+        B200_CHECK(lower[f] >= 0 && upper[f] < nCells && lower[f] < upper[f], "addressing is not upper-triangular");
+        if (f > 0) B200_CHECK(lower[f - 1] <= lower[f], "lowerAddr is not sorted (upper-triangular order required)");
+    }
+    // row table: faces where the cell is the upper address (ascending), then owned faces (ascending)
+    std::vector<int> rowStart(nCells + 1, 0), rowMid(nCells, 0);
+    std::vector<int> cntL(nCells, 0), cntU(nCells, 0);
+    for (int f = 0; f < nFaces; f++) { cntL[upper[f]]++; cntU[lower[f]]++; }
+    for (int cI = 0; cI < nCells; cI++) { rowStart[cI + 1] = rowStart[cI] + cntL[cI] + cntU[cI]; rowMid[cI] = rowStart[cI] + cntL[cI]; }
+    std::vector<int> rowCol(2 * (size_t)nFaces), rowFace(2 * (size_t)nFaces);
+    {
+        std::vector<int> posL(rowStart.begin(), rowStart.end() - 1), posU(rowMid);
+        for (int f = 0; f < nFaces; f++) {
+            int e = posL[upper[f]]++; rowCol[e] = lower[f]; rowFace[e] = f;
+            e = posU[lower[f]]++; rowCol[e] = upper[f]; rowFace[e] = f;
+        }
+    }
+    // level schedule of the lower-neighbour DAG and the level-renumbered cell list
+    std::vector<int> level(nCells, 0);
+    nLevels = nCells ? 1 : 0;
+    for (int f = 0; f < nFaces; f++) {
+        const int l = level[lower[f]] + 1;
+        if (l > level[upper[f]]) level[upper[f]] = l;
+        nLevels = std::max(nLevels, l + 1);
+    }
+    h_lvlStart.assign(nLevels + 1, 0);
+    for (int cI = 0; cI < nCells; cI++) h_lvlStart[level[cI] + 1]++;
+    for (int L = 0; L < nLevels; L++) { maxLevelSize = std::max(maxLevelSize, h_lvlStart[L + 1]); h_lvlStart[L + 1] += h_lvlStart[L]; }
+    std::vector<int> lvlCells(nCells);
+    {
+        std::vector<int> pos(h_lvlStart.begin(), h_lvlStart.end() - 1);
+        for (int cI = 0; cI < nCells; cI++) lvlCells[pos[level[cI]]++] = cI;
+    }
+    h_level = level;
+    cudaStream_t s = ctx->stream;
+    d_lower = dev_alloc<int>(nFaces); d_upper = dev_alloc<int>(nFaces);
+    d_rowStart = dev_alloc<int>(nCells + 1); d_rowMid = dev_alloc<int>(nCells);
+    d_rowCol = dev_alloc<int>(2 * (size_t)nFaces); d_rowFace = dev_alloc<int>(2 * (size_t)nFaces);
+    d_lvlCells = dev_alloc<int>(nCells); d_lvlStart = dev_alloc<int>(nLevels + 1);
+    h2d(d_lower, lower, nFaces, s); h2d(d_upper, upper, nFaces, s);
+    h2d(d_rowStart, rowStart.data(), nCells + 1, s); h2d(d_rowMid, rowMid.data(), nCells, s);
+    h2d(d_rowCol, rowCol.data(), rowCol.size(), s); h2d(d_rowFace, rowFace.data(), rowFace.size(), s);
+    h2d(d_lvlCells, lvlCells.data(), nCells, s); h2d(d_lvlStart, h_lvlStart.data(), nLevels + 1, s);
+    for (int p = 0; p < nInterfaces; p++) {
+        DevInterface it;
+        it.size = ifaceSize[p]; it.neighbRank = ifaceNeighbRank[p];
+        it.faceCells = dev_alloc<int>(it.size);
+        h2d(it.faceCells, ifaceFaceCells[p], it.size, s);
+        it.recvBuf = dev_alloc<double>(it.size); it.sendBuf = dev_alloc<double>(it.size);
+        std::vector<int> sorted(ifaceFaceCells[p], ifaceFaceCells[p] + it.size);
+        std::sort(sorted.begin(), sorted.end());
+        it.hasDuplicates = std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end();
+        ifaces.push_back(it);
+    }
+    ctx->sync();
+}
+
+Ldu::Ldu(Ctx* c, BlockDims d) : ctx(c), dims(d)
+{
+    B200_CHECK(d.nCells() < (int64_t)INT32_MAX && d.nFaces() < (int64_t)INT32_MAX, "block too large for int32 labels");
+    nCells = (int)d.nCells(); nFaces = (int)d.nFaces();
+    isBlock = true; hasGeneral = false;
+    nLevels = d.nx + d.ny + d.nz - 2;
+}
+
+Ldu::~Ldu()
+{
+    dev_free(d_lower); dev_free(d_upper); dev_free(d_rowStart); dev_free(d_rowMid); dev_free(d_rowCol); dev_free(d_rowFace);
+    dev_free(d_lvlCells); dev_free(d_lvlStart);
+    for (auto& it : ifaces) { dev_free(it.faceCells); dev_free(it.recvBuf); dev_free(it.sendBuf); }
+    for (auto& w : work) dev_free(w);
+    dev_free(rD); dev_free(d_sumA);
+    dev_free(d_state);
+    if (h_state) cudaFreeHost(h_state);
+    dev_free(red.partials); dev_free(red.ticket); dev_free(red.result);
+    for (auto& p : stage) dev_free(p);
+}
+
+void Ldu::setBlock(int nx, int ny, int nz)
+{
+    BlockDims d; d.nx = nx; d.ny = ny; d.nz = nz;
+    B200_CHECK(nx > 0 && ny > 0 && nz > 0, "block dimensions must be positive");
+    B200_CHECK(d.nCells() == nCells && d.nFaces() == nFaces, "block dimensions do not match nCells/nFaces");
+    // expand the closed form on the device and compare bit-exactly with the addressing given at creation
+    int* lo = dev_alloc<int>(nFaces); int* up = dev_alloc<int>(nFaces);
+    k_block_addressing<<<std::min(ny * nz, 4096), BLK, 0, ctx->stream>>>(d, lo, up);
+    B200_LAUNCH_CHECK();
+    std::vector<int> hl(nFaces), hu(nFaces);
+    d2h(hl.data(), lo, nFaces, ctx->stream); d2h(hu.data(), up, nFaces, ctx->stream);
+    ctx->sync();
+    dev_free(lo); dev_free(up);
+    B200_CHECK(hl == h_lower && hu == h_upper, "addressing is not a single blockMesh hex block of these dimensions");
+    dims = d; isBlock = true;
+    for (auto& w : work) dev_free(w);       // ghost padding changes
+    dev_free(rD);
+}
+
+void Ldu::levels(int* levelOfCell, int* nLev)
+{
+    if (hasGeneral) {
+        std::memcpy(levelOfCell, h_level.data(), sizeof(int) * nCells);
+    } else {
+        for (int k = 0; k < dims.nz; k++) for (int j = 0; j < dims.ny; j++) for (int i = 0; i < dims.nx; i++)
+            levelOfCell[i + dims.nx * (j + dims.ny * k)] = i + j + k;
+    }
+    *nLev = nLevels;
+}
+
+void Ldu::ensureWork()
+{
+    if (!d_state) {
+        d_state = dev_alloc<SolveState>(1);
+        B200_CUDA(cudaMallocHost(&h_state, sizeof(SolveState)));
+        red.partials = dev_alloc<double>((size_t)S_NSLOTS * RED_MAX_BLOCKS);
+        red.ticket = dev_alloc<unsigned>(1);
+        red.result = dev_alloc<double>(S_NSLOTS);
+        B200_CUDA(cudaMemsetAsync(red.ticket, 0, sizeof(unsigned), ctx->stream));
+        B200_CUDA(cudaMemsetAsync(red.result, 0, sizeof(double) * S_NSLOTS, ctx->stream));
+    }
+    if (!work[0]) {
+        ghost = isBlock ? (int64_t)dims.nx * dims.ny : 0;
+        const size_t len = (size_t)nCells + 2 * (size_t)ghost;
+        for (auto& w : work) { w = dev_alloc<double>(len); B200_CUDA(cudaMemsetAsync(w, 0, len * sizeof(double), ctx->stream)); }
+        rD = dev_alloc<double>(len);
+        B200_CUDA(cudaMemsetAsync(rD, 0, len * sizeof(double), ctx->stream));
+    }
+    redBlocks = std::min(ctx->persistentBlocks(), red_blocks_for(std::max(nCells, 1)));
+}
+
+// ------------------------------------------------------------------ halo / interface update
+void Ldu::exchange(const double* x)
+{
+    if (ctx->nranks <= 1) return;
+    if (isBlock && (ghostBelow || ghostAbove)) {
+        const size_t plane = (size_t)dims.nx * dims.ny;
+        double* xw = const_cast<double*>(x);
+        ctx->sendrecv(x, xw - plane, ghostBelow ? ctx->rank - 1 : -1, x + (size_t)(dims.nz - 1) * plane, xw + (size_t)dims.nz * plane,
+                      ghostAbove ? ctx->rank + 1 : -1, plane);
+        return;
+    }
+    if (ifaces.empty()) return;
+    for (auto& it : ifaces) {
+        k_iface_gather<<<std::max(1, std::min((it.size + BLK - 1) / BLK, 1024)), BLK, 0, ctx->stream>>>(it.size, it.faceCells, x, it.sendBuf);
+        B200_LAUNCH_CHECK();
+    }
+    B200_NCCL(ncclGroupStart());
+    for (auto& it : ifaces) {
+        B200_NCCL(ncclSend(it.sendBuf, it.size, ncclDouble, it.neighbRank, ctx->comm, ctx->stream));
+        B200_NCCL(ncclRecv(it.recvBuf, it.size, ncclDouble, it.neighbRank, ctx->comm, ctx->stream));
+    }
+    B200_NCCL(ncclGroupEnd());
+}
+
+void Ldu::allreduce(int slot0, int n, bool)
+{
+    ctx->allreduceSum(red.result + slot0, n);
+}
+
+// ------------------------------------------------------------------ Amul
+template <int MODE> static void launch_amul(Ldu& L, const MatrixView& A, const double* x, double* y, const double* aux, const SolveState* st)
+{
+    cudaStream_t s = L.ctx->stream;
+    if (L.isBlock) {
+        const double* bb = (L.ghostBelow && A.bouCoeffs) ? A.bouCoeffs[0] : nullptr;
+        const double* ba = (L.ghostAbove && A.bouCoeffs) ? A.bouCoeffs[L.ghostBelow ? 1 : 0] : nullptr;
+        const int64_t items = (int64_t)((L.dims.nx + BLK - 1) / BLK) * L.dims.ny * L.dims.nz;
+        const int grid = (int)std::min<int64_t>(items, L.ctx->persistentBlocks());
+        k_amul_block<MODE><<<grid, BLK, 0, s>>>(L.dims, A.diag, A.upper, A.lower, x, y, aux, bb, ba, L.red, st);
+    } else {
+        k_amul_general<MODE><<<L.redBlocks, BLK, 0, s>>>(L.nCells, L.d_rowStart, L.d_rowMid, L.d_rowCol, L.d_rowFace, A.diag, A.upper,
+                                                         A.lower, x, y, aux, L.red, st);
+    }
+    B200_LAUNCH_CHECK();
+}
+
+void Ldu::amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux)
+{
+    const SolveState* st = d_state;
+    exchange(x);
+    const bool post = !ifaces.empty();       // general coupled interfaces: apply after the gather, reduce separately
+    const int m = post ? AM_NONE : mode;
+    switch (m) {
+    case AM_NONE: launch_amul<AM_NONE>(*this, A, x, y, aux, st); break;
+    case AM_SUMX: launch_amul<AM_SUMX>(*this, A, x, y, aux, st); break;
+    case AM_DOT_YX: launch_amul<AM_DOT_YX>(*this, A, x, y, aux, st); break;
+    case AM_DOT_AUXY: launch_amul<AM_DOT_AUXY>(*this, A, x, y, aux, st); break;
+    case AM_TT_TS: launch_amul<AM_TT_TS>(*this, A, x, y, aux, st); break;
+    }
+    if (!post) return;
+    cudaStream_t s = ctx->stream;
+    for (size_t p = 0; p < ifaces.size(); p++) {
+        auto& it = ifaces[p];
+        const int grid = it.hasDuplicates ? 1 : std::max(1, std::min((it.size + BLK - 1) / BLK, 1024));
+        k_iface_apply<<<grid, BLK, 0, s>>>(it.size, it.faceCells, A.bouCoeffs[p], it.recvBuf, y, it.hasDuplicates ? 1 : 0, st);
+        B200_LAUNCH_CHECK();
+    }
+    const int64_t n = nCells;
+    if (mode == AM_SUMX) { k_sum<<<redBlocks, BLK, 0, s>>>(n, x, red, S_SUMPSI); B200_LAUNCH_CHECK(); }
+    else if (mode == AM_DOT_YX) { k_dot<<<redBlocks, BLK, 0, s>>>(n, y, x, red, S_DEN, st); B200_LAUNCH_CHECK(); }
+    else if (mode == AM_DOT_AUXY) { k_dot<<<redBlocks, BLK, 0, s>>>(n, aux, y, red, S_DEN, st); B200_LAUNCH_CHECK(); }
+    else if (mode == AM_TT_TS) {
+        k_dot<<<redBlocks, BLK, 0, s>>>(n, y, y, red, S_TT, st); B200_LAUNCH_CHECK();
+        k_dot<<<redBlocks, BLK, 0, s>>>(n, y, aux, red, S_TS, st); B200_LAUNCH_CHECK();
+    }
+}
+
+void Ldu::amul(const MatrixView& A, const double* psi, double* Apsi)
+{
+    ensureWork();
+    B200_CUDA(cudaMemsetAsync(d_state, 0, sizeof(SolveState), ctx->stream));
+    amulFused(A, psi, Apsi, AM_NONE, nullptr);
+}
+
+// ------------------------------------------------------------------ preconditioners
+void Ldu::factor(int kind, const MatrixView& A)
+{
+    cudaStream_t s = ctx->stream;
+    const SolveState* st = d_state;
+    if (kind == 0) return;
+    if (kind == 1) {
+        k_copy<<<redBlocks, BLK, 0, s>>>((int64_t)nCells, A.diag, rD + ghost, st); B200_LAUNCH_CHECK();
+    } else {
+        const bool dilu = kind == 3;
+        double* rd = rD + ghost;
+        const double* nul = nullptr; double* nulw = nullptr;
+        if (isBlock) {
+            if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
+            else coop_launch(ctx, k_sweep_block<0, false, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
+        } else {
+            const int* ls = d_lvlStart;
+            if (dilu) coop_launch(ctx, k_sweep_general<0, true, false>, (int64_t)maxLevelSize, nLevels, ls, (const int*)d_lvlCells, (const int*)d_rowStart, (const int*)d_rowMid, (const int*)d_rowCol, (const int*)d_rowFace, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
+            else coop_launch(ctx, k_sweep_general<0, false, false>, (int64_t)maxLevelSize, nLevels, ls, (const int*)d_lvlCells, (const int*)d_rowStart, (const int*)d_rowMid, (const int*)d_rowCol, (const int*)d_rowFace, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
+        }
+    }
+    k_reciprocal<<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rD + ghost, st); B200_LAUNCH_CHECK();
+}
+
+// wA = M^-1 rA, optionally with sum(wA . dotVec) into slot S_RHO
+void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int doDot, const double* dotVec)
+{
+    cudaStream_t s = ctx->stream;
+    const SolveState* st = d_state;
+    double* rd = rD + ghost;
+    if (kind == 0) { k_precond_pointwise<false><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
+    if (kind == 1) { k_precond_pointwise<true><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
+    const bool dilu = kind == 3;
+    const double* nul = nullptr;
+    if (isBlock) {
+        const int64_t work_ = (int64_t)dims.ny * dims.nz;
+        if (dilu) coop_launch(ctx, k_sweep_block<1, true, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+        else coop_launch(ctx, k_sweep_block<1, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+        if (doDot) coop_launch(ctx, k_sweep_block<2, false, true>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st);
+        else coop_launch(ctx, k_sweep_block<2, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+    } else {
+        const int* ls = d_lvlStart; const int* lc = d_lvlCells; const int* rs = d_rowStart; const int* rm = d_rowMid;
+        const int* rc = d_rowCol; const int* rf = d_rowFace;
+        const int64_t work_ = maxLevelSize;
+        if (dilu) coop_launch(ctx, k_sweep_general<1, true, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+        else coop_launch(ctx, k_sweep_general<1, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+        if (doDot) coop_launch(ctx, k_sweep_general<2, false, true>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st);
+        else coop_launch(ctx, k_sweep_general<2, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+    }
+}
+
+void Ldu::precondition(int kind, const MatrixView& A, const double* rA, double* wA)
+{
+    ensureWork();
+    B200_CUDA(cudaMemsetAsync(d_state, 0, sizeof(SolveState), ctx->stream));
+    factor(kind, A);
+    applyPrecond(kind, A, rA, wA, 0, nullptr);
+}
+
+// ------------------------------------------------------------------ Krylov drivers
+static void ctrl(Ldu& L, int phase)
+{
+    k_ctrl<<<1, 1, 0, L.ctx->stream>>>(phase, L.d_state, L.red.result, &L.d_state->early);
+    B200_LAUNCH_CHECK();
+}
+
+SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, const SolveControls& sc)
+{
+    ensureWork();
+    cudaStream_t s = ctx->stream;
+    const int64_t n = nCells;
+    SolvePerf perf;
+    if (sc.solver == 2) {       // diagonalSolver
+        k_diag_solve<<<redBlocks, BLK, 0, s>>>(n, A.diag, source, psi); B200_LAUNCH_CHECK();
+        perf.converged = 1;
+        return perf;
+    }
+    std::memset(h_state, 0, sizeof(SolveState));
+    h_state->tol = sc.tolerance; h_state->relTol = sc.relTol; h_state->minIter = sc.minIter; h_state->maxIter = sc.maxIter;
+    double nGlobal = (double)n;
+    if (ctx->nranks > 1) {
+        // global cell count for gAverage(psi): one tiny allreduce per solve
+        B200_CUDA(cudaMemcpyAsync(red.result + S_NSLOTS - 1, &nGlobal, sizeof(double), cudaMemcpyHostToDevice, s));
+        ctx->allreduceSum(red.result + S_NSLOTS - 1, 1);
+        B200_CUDA(cudaMemcpyAsync(&nGlobal, red.result + S_NSLOTS - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+        ctx->sync();
+    }
+    h_state->nGlobal = nGlobal;
+    h2d(d_state, h_state, 1, s);
+    const SolveState* st = d_state;
+
+    const bool pcg = sc.solver == 0;
+    double *wA = vec(0), *pA = vec(1), *rA = vec(2), *qA = vec(3);
+    double *yA = vec(0), *AyA = vec(3), *sA = vec(4), *zA = vec(5), *tA = vec(6), *rA0 = vec(7);
+
+    // wA = A psi (+ sum psi); rA = source - wA; normFactor
+    amulFused(A, psi, wA, AM_SUMX, nullptr);
+    allreduce(S_SUMPSI, 1);
+    ctrl(*this, C_AVG);
+    if (isBlock) {
+        const double* bb = (ghostBelow && A.bouCoeffs) ? A.bouCoeffs[0] : nullptr;
+        const double* ba = (ghostAbove && A.bouCoeffs) ? A.bouCoeffs[ghostBelow ? 1 : 0] : nullptr;
+        const int64_t items = (int64_t)((dims.nx + BLK - 1) / BLK) * dims.ny * dims.nz;
+        const int grid = (int)std::min<int64_t>(items, ctx->persistentBlocks());
+        B200_CHECK(ifaces.empty(), "block addressing with general interfaces: use ghost planes");
+        k_normfactor_block<<<grid, BLK, 0, s>>>(dims, A.diag, A.upper, A.lower, bb, ba, source, wA, rA, red, st);
+        B200_LAUNCH_CHECK();
+    } else {
+        if (!d_sumA) d_sumA = dev_alloc<double>(n);
+        k_sumA_general<<<redBlocks, BLK, 0, s>>>(nCells, d_rowStart, d_rowMid, d_rowFace, A.diag, A.upper, A.lower, d_sumA);
+        B200_LAUNCH_CHECK();
+        for (size_t p = 0; p < ifaces.size(); p++) {
+            auto& it = ifaces[p];
+            const int grid = it.hasDuplicates ? 1 : std::max(1, std::min((it.size + BLK - 1) / BLK, 1024));
+            k_iface_sumA<<<grid, BLK, 0, s>>>(it.size, it.faceCells, A.bouCoeffs[p], d_sumA, it.hasDuplicates ? 1 : 0);
+            B200_LAUNCH_CHECK();
+        }
+        k_normfactor_general<<<redBlocks, BLK, 0, s>>>(nCells, d_sumA, source, wA, rA, red, st);
+        B200_LAUNCH_CHECK();
+    }
+    allreduce(S_NORM, 2);
+    ctrl(*this, C_INIT);
+    factor(sc.precond, A);
+    if (!pcg) { k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); }
+
+    const int hardMax = std::max(sc.maxIter + 1, sc.minIter);
+    int enqueued = 0, chunk = 2;
+    for (;;) {
+        for (int it = 0; it < chunk && enqueued < hardMax; it++, enqueued++) {
+            if (pcg) {
+                applyPrecond(sc.precond, A, rA, wA, 1, rA);         // wA = M^-1 rA ; wArA
+                allreduce(S_RHO, 1);
+                ctrl(*this, C_PCG_BETA);
+                k_pcg_p<<<redBlocks, BLK, 0, s>>>(n, wA, pA, st); B200_LAUNCH_CHECK();
+                amulFused(A, pA, qA, AM_DOT_YX, nullptr);           // q = A pA ; wApA
+                allreduce(S_DEN, 1);
+                ctrl(*this, C_PCG_ALPHA);
+                k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, red, st); B200_LAUNCH_CHECK();
+                allreduce(S_MAGR, 1);
+                ctrl(*this, C_ITER_END);
+            } else {
+                k_dot<<<redBlocks, BLK, 0, s>>>(n, rA0, rA, red, S_RHO, st); B200_LAUNCH_CHECK();
+                allreduce(S_RHO, 1);
+                ctrl(*this, C_BICG_RHO);
+                k_bicg_p<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, pA, st); B200_LAUNCH_CHECK();
+                applyPrecond(sc.precond, A, pA, yA, 0, nullptr);
+                amulFused(A, yA, AyA, AM_DOT_AUXY, rA0);            // rA0 . AyA
+                allreduce(S_DEN, 1);
+                ctrl(*this, C_BICG_ALPHA);
+                k_bicg_s<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, sA, red, st); B200_LAUNCH_CHECK();
+                allreduce(S_MAGR, 1);
+                ctrl(*this, C_BICG_SCHECK);
+                k_bicg_early<<<redBlocks, BLK, 0, s>>>(n, yA, psi, st, &d_state->early); B200_LAUNCH_CHECK();
+                ctrl(*this, C_BICG_EARLY_END);
+                applyPrecond(sc.precond, A, sA, zA, 0, nullptr);
+                amulFused(A, zA, tA, AM_TT_TS, sA);                 // tA.tA, tA.sA
+                allreduce(S_TT, 2);
+                ctrl(*this, C_BICG_OMEGA);
+                k_bicg_update<<<redBlocks, BLK, 0, s>>>(n, yA, zA, sA, tA, psi, rA, red, st); B200_LAUNCH_CHECK();
+                allreduce(S_MAGR2, 1);
+                ctrl(*this, C_ITER_END2);
+            }
+        }
+        d2h(h_state, d_state, 1, s);
+        ctx->sync();
+        if (h_state->done || enqueued >= hardMax) break;
+        chunk = std::min(chunk * 2, 32);
+    }
+    perf.initialResidual = h_state->initRes; perf.finalResidual = h_state->finalRes;
+    perf.nIterations = h_state->nIter; perf.converged = h_state->converged; perf.singular = h_state->singular;
+    return perf;
+}
+
+} // namespace b200

@@ -1,0 +1,500 @@
+#include "thermal_kernels.cuh"
+#include <algorithm>
+#include <cstring>
+#include <climits>
+
+namespace b200 {
+
+static const double kSmall = 1e-15, kVGreat = 1e300;
+
+// SOLVER/interpolateXY/interpolateXY.C:33-109 (host scalar; used for Tliq/Tsol and the initial alpha.solid)
+static double interpolateXY(double x, const std::vector<double>& xOld, const std::vector<double>& yOld)
+{
+    const int n = (int)xOld.size();
+    int lo = 0;
+    for (lo = 0; lo < n && xOld[lo] > x; ++lo) {}
+    int low = lo;
+    if (low < n) for (int i = low; i < n; ++i) if (xOld[i] > xOld[lo] && xOld[i] <= x) lo = i;
+    int hi = 0;
+    for (hi = 0; hi < n && xOld[hi] < x; ++hi) {}
+    int high = hi;
+    if (high < n) for (int i = high; i < n; ++i) if (xOld[i] < xOld[hi] && xOld[i] >= x) hi = i;
+    if (lo < n && hi < n && lo != hi) return yOld[lo] + ((x - xOld[lo]) / (xOld[hi] - xOld[lo])) * (yOld[hi] - yOld[lo]);
+    if (lo == hi) return yOld[lo];
+    if (lo == n) return yOld[hi];
+    return yOld[lo];
+}
+
+double* ThermalCase::allocField()
+{
+    double* p = dev_alloc<double>(padded);
+    B200_CUDA(cudaMemsetAsync(p, 0, padded * sizeof(double), ctx->stream));
+    allocs.push_back(p);
+    return p + plane;
+}
+
+static int cells_grid(Ctx* ctx, const BlockDims& d)
+{
+    const int64_t items = (int64_t)((d.nx + BLK - 1) / BLK) * d.ny * d.nz;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(items, ctx->persistentBlocks()));
+}
+static int flat_grid(Ctx* ctx, int64_t n)
+{
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + BLK - 1) / BLK, ctx->persistentBlocks()));
+}
+
+ThermalCase::ThermalCase(Ctx* c, const b200_case_desc& desc) : ctx(c)
+{
+    ctl = desc.controls; mat = desc.material;
+    B200_CHECK(mat.nThermo >= 2 && mat.nThermo <= 1024, "thermoPath needs 2..1024 rows");
+    thermoT.assign(mat.thermoT, mat.thermoT + mat.nThermo);
+    thermoA.assign(mat.thermoAlpha, mat.thermoAlpha + mat.nThermo);
+    mat.thermoT = thermoT.data(); mat.thermoAlpha = thermoA.data();
+    Tliq = interpolateXY(0.0, thermoA, thermoT);      // createFields.H:59-71
+    Tsol = interpolateXY(1.0, thermoA, thermoT);
+    Tinitial = desc.Tinitial;
+    patches.assign(desc.patches, desc.patches + desc.nPatches);
+    const b200_block_mesh& bm = desc.mesh;
+    B200_CHECK(bm.nx > 0 && bm.ny > 0 && bm.nz > 0, "mesh dimensions must be positive");
+    const int R = ctx->nranks, r = ctx->rank;
+    B200_CHECK(R <= bm.nz, "more ranks than z layers");
+    const int kBeg = (int)((int64_t)bm.nz * r / R), kEnd = (int)((int64_t)bm.nz * (r + 1) / R);
+    dims.nx = bm.nx; dims.ny = bm.ny; dims.nz = kEnd - kBeg; nzGlobal = bm.nz;
+    rankBelow = r > 0 ? r - 1 : -1; rankAbove = r < R - 1 ? r + 1 : -1;
+    geo.ox = bm.min[0]; geo.oy = bm.min[1]; geo.oz = bm.min[2];
+    geo.dx = (bm.max[0] - bm.min[0]) / bm.nx; geo.dy = (bm.max[1] - bm.min[1]) / bm.ny; geo.dz = (bm.max[2] - bm.min[2]) / bm.nz;
+    geo.V = geo.dx * geo.dy * geo.dz;
+    geo.sfx = geo.dy * geo.dz; geo.sfy = geo.dx * geo.dz; geo.sfz = geo.dx * geo.dy;
+    geo.dcx = 1.0 / geo.dx; geo.dcy = 1.0 / geo.dy; geo.dcz = 1.0 / geo.dz;
+    geo.bcx = 1.0 / (0.5 * geo.dx); geo.bcy = 1.0 / (0.5 * geo.dy); geo.bcz = 1.0 / (0.5 * geo.dz);
+    geo.k0 = kBeg;
+    plane = (size_t)dims.nx * dims.ny;
+    padded = (size_t)dims.nCells() + 2 * plane;
+
+    cudaStream_t s = ctx->stream;
+    T = allocField(); Told = allocField(); alpha1 = allocField(); alpha1old = allocField(); alpha3 = allocField();
+    kappa = allocField(); rKappa = allocField(); Cp = allocField(); qDot = allocField();
+    dFdT = allocField(); T0 = allocField(); diag0 = allocField(); source0 = allocField(); diag = allocField(); source = allocField();
+    upper = dev_alloc<double>((size_t)dims.nFaces() + 1);
+    red.partials = dev_alloc<double>((size_t)R_NSLOTS * RED_MAX_BLOCKS);
+    red.ticket = dev_alloc<unsigned>(1);
+    red.result = dev_alloc<double>(R_NSLOTS);
+    B200_CUDA(cudaMemsetAsync(red.ticket, 0, sizeof(unsigned), s));
+    B200_CUDA(cudaMemsetAsync(red.result, 0, sizeof(double) * R_NSLOTS, s));
+    B200_CUDA(cudaMallocHost(&h_red, sizeof(double) * R_NSLOTS));
+    d_thermo = dev_alloc<double>(2 * (size_t)mat.nThermo);
+    h2d(d_thermo, thermoT.data(), mat.nThermo, s);
+    h2d(d_thermo + mat.nThermo, thermoA.data(), mat.nThermo, s);
+
+    // the six sides: physical patches in patch order, then processor sides (below, above)
+    int nOrder = 0;
+    for (int q = 0; q < 6; q++) { sides[q] = SideInfo(); sidesDev.order[q] = 0; }
+    bool assigned[6] = {false, false, false, false, false, false};
+    patchUpdated.assign(patches.size(), false);
+    auto sideCount = [&](int sd) { return sd <= B200_XMAX ? dims.ny * dims.nz : sd <= B200_YMAX ? dims.nx * dims.nz : dims.nx * dims.ny; };
+    for (size_t p = 0; p < patches.size(); p++) {
+        const b200_patch& ps = patches[p];
+        for (int q = 0; q < ps.nSides; q++) {
+            const int sd = ps.sides[q];
+            B200_CHECK(sd >= 0 && sd < 6 && !assigned[sd], "block side listed twice or out of range");
+            assigned[sd] = true;
+            if ((sd == B200_ZMIN && rankBelow >= 0) || (sd == B200_ZMAX && rankAbove >= 0)) continue;   // not on this rank
+            SideInfo& si = sides[sd];
+            si.type = ps.type; si.patch = (int)p; si.value = ps.value; si.h = ps.h; si.emissivity = ps.emissivity; si.Tinf = ps.Tinf;
+            sidesDev.order[nOrder++] = sd;
+        }
+    }
+    for (int sd = 0; sd < 6; sd++) B200_CHECK(assigned[sd], "every block side must belong to a patch");
+    if (rankBelow >= 0) { sides[B200_ZMIN].type = SIDE_PROCESSOR; sidesDev.order[nOrder++] = B200_ZMIN; }
+    if (rankAbove >= 0) { sides[B200_ZMAX].type = SIDE_PROCESSOR; sidesDev.order[nOrder++] = B200_ZMAX; }
+    sidesDev.nOrder = nOrder;
+    for (int sd = 0; sd < 6; sd++) {
+        SideInfo& si = sides[sd];
+        si.n = sideCount(sd);
+        si.valueFraction = dev_alloc<double>(si.n); si.Tb = dev_alloc<double>(si.n);
+        si.intCoeff = dev_alloc<double>(si.n); si.bouCoeff = dev_alloc<double>(si.n);
+        B200_CUDA(cudaMemsetAsync(si.valueFraction, 0, sizeof(double) * si.n, s));
+        B200_CUDA(cudaMemsetAsync(si.intCoeff, 0, sizeof(double) * si.n, s));
+        B200_CUDA(cudaMemsetAsync(si.bouCoeff, 0, sizeof(double) * si.n, s));
+        k_fill<<<flat_grid(ctx, si.n), BLK, 0, s>>>(si.n, si.Tb, si.type == B200_BC_FIXED_VALUE ? si.value : Tinitial);
+        B200_LAUNCH_CHECK();
+        sidesDev.type[sd] = si.type; sidesDev.intCoeff[sd] = si.intCoeff; sidesDev.bouCoeff[sd] = si.bouCoeff;
+        sidesDev.valueFraction[sd] = si.valueFraction; sidesDev.Tb[sd] = si.Tb; sidesDev.Tinf[sd] = si.Tinf;
+    }
+    // 0/T `value uniform` entries: the tutorials give the internal value; fixedValue faces hold their own value
+    for (int sd = 0; sd < 6; sd++)
+        if (sides[sd].type != B200_BC_FIXED_VALUE) { k_fill<<<flat_grid(ctx, sides[sd].n), BLK, 0, s>>>(sides[sd].n, sides[sd].Tb, Tinitial); B200_LAUNCH_CHECK(); }
+
+    // fields: T uniform, alpha.solid from the thermoPath table (createFields.H:74-78), alpha.powder box
+    const int64_t n = dims.nCells();
+    k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, T, Tinitial); B200_LAUNCH_CHECK();
+    k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, Told, Tinitial); B200_LAUNCH_CHECK();
+    const double a0 = std::min(std::max(interpolateXY(Tinitial, thermoT, thermoA), 0.0), 1.0);
+    k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, alpha1, a0); B200_LAUNCH_CHECK();
+    k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, alpha1old, a0); B200_LAUNCH_CHECK();
+    for (int k = 0; k < dims.nz; k++) {
+        const double cz = geo.oz + (k + geo.k0 + 0.5) * geo.dz;
+        if (cz > desc.powderZMin) { k_fill<<<flat_grid(ctx, (int64_t)plane), BLK, 0, s>>>((int64_t)plane, alpha3 + (size_t)k * plane, 1.0); B200_LAUNCH_CHECK(); }
+    }
+    time_ = ctl.startTime; deltaT_ = ctl.deltaT;
+    for (int b = 0; b < desc.nBeams; b++) sources.emplace_back(desc.beams[b], time_, ctl.endTime);
+
+    ldu.reset(new Ldu(ctx, dims));
+    ldu->ghostBelow = rankBelow >= 0; ldu->ghostAbove = rankAbove >= 0;
+    int nb = 0;
+    if (rankBelow >= 0) bouPtrs[nb++] = sides[B200_ZMIN].bouCoeff;
+    if (rankAbove >= 0) bouPtrs[nb++] = sides[B200_ZMAX].bouCoeff;
+
+    double a, b2, c2;
+    updatePropertiesAndNumbers(a, b2, c2);            // createFields.H:112
+    ctx->sync();
+}
+
+ThermalCase::~ThermalCase()
+{
+    cudaStreamSynchronize(ctx->stream);
+    for (double* p : allocs) cudaFree(p);
+    dev_free(upper); dev_free(wbuf); dev_free(d_thermo);
+    dev_free(red.partials); dev_free(red.ticket); dev_free(red.result);
+    if (h_red) cudaFreeHost(h_red);
+    for (auto& si : sides) { dev_free(si.valueFraction); dev_free(si.Tb); dev_free(si.intCoeff); dev_free(si.bouCoeff); }
+}
+
+double* ThermalCase::field(int f)
+{
+    switch (f) {
+    case B200_FIELD_T: return T;
+    case B200_FIELD_ALPHA_SOLID: return alpha1;
+    case B200_FIELD_ALPHA_POWDER: return alpha3;
+    case B200_FIELD_KAPPA: return kappa;
+    case B200_FIELD_CP: return Cp;
+    case B200_FIELD_QDOT: return qDot;
+    case B200_FIELD_DFDT: return dFdT;
+    case B200_FIELD_T0: return T0;
+    }
+    throw Error("unknown field id");
+}
+
+void ThermalCase::getField(int f, double* out)
+{
+    d2h(out, field(f), (size_t)dims.nCells(), ctx->stream);
+    ctx->sync();
+}
+
+void ThermalCase::setField(int f, const double* in)
+{
+    const size_t n = (size_t)dims.nCells();
+    h2d(field(f), in, n, ctx->stream);
+    if (f == B200_FIELD_T) {
+        B200_CUDA(cudaMemcpyAsync(Told, T, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        evaluateT();
+    }
+    if (f == B200_FIELD_ALPHA_SOLID) B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->sync();
+}
+
+void ThermalCase::haloExchange(double* f)
+{
+    if (ctx->nranks <= 1) return;
+    ctx->sendrecv(f, f - plane, rankBelow, f + (size_t)(dims.nz - 1) * plane, f + (size_t)dims.nz * plane, rankAbove, plane);
+}
+
+void ThermalCase::readReductions(int n)
+{
+    d2h(h_red, red.result, n, ctx->stream);
+    ctx->sync();
+}
+
+// updateProperties.H + the two numbers of setDeltaT.H (alphaCoNum without dt history issues, DiNum/dt)
+void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1)
+{
+    cudaStream_t s = ctx->stream;
+    MatDev m;
+    std::memcpy(m.kappa, mat.kappa, sizeof(m.kappa)); std::memcpy(m.Cp, mat.Cp, sizeof(m.Cp));
+    m.rho = mat.rho; m.Lf = mat.Lf; m.Tliq = Tliq; m.Tsol = Tsol;
+    k_props<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, m, T, Told, alpha1, alpha3, kappa, rKappa, Cp, 1.0 / deltaT_, deltaT_, red);
+    B200_LAUNCH_CHECK();
+    haloExchange(kappa);
+    haloExchange(rKappa);
+    k_dinum<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, geo, sidesDev, kappa, Cp, mat.rho, red);
+    B200_LAUNCH_CHECK();
+    if (ctx->nranks > 1) {
+        ctx->allreduceMax(red.result + R_ALPHACO, 1);
+        ctx->allreduceMin(red.result + R_MINALPHA, 1);
+        ctx->allreduceMax(red.result + R_DIMAX, 1);
+    }
+    readReductions(3);
+    alphaCoMax = h_red[R_ALPHACO]; minAlpha1 = h_red[R_MINALPHA]; diMax = h_red[R_DIMAX];
+}
+
+// SOLVER/setDeltaT.H:1-50 and [UPSTREAM] Time::adjustDeltaT (adjustableRunTime write snapping)
+void ThermalCase::setDeltaT(double alphaCoMax, double diMax)
+{
+    if (!ctl.adjustTimeStep) return;
+    alphaCoNum = alphaCoMax;
+    DiNum = diMax * deltaT_;
+    const double CoNum = 0.0;          // CourantNo.H with phi == 0
+    const double maxDeltaTFact = std::min(std::min(ctl.maxCo / (CoNum + kSmall), ctl.maxAlphaCo / (alphaCoNum + kSmall)),
+                                          ctl.maxDi / (DiNum + kSmall));
+    const double deltaTFact = std::min(std::min(maxDeltaTFact, 1.0 + 0.1 * maxDeltaTFact), 1.2);
+    double dt = std::min(deltaTFact * deltaT_, ctl.maxDeltaT);
+    for (auto& hs : sources) hs.beam.adjustDeltaT(dt, time_);      // movingHeatSourceModel.C:92-98
+    deltaT_ = dt;
+    if (ctl.writeInterval > 0) {
+        const double timeToNextWrite = std::max(0.0, (writeTimeIndex + 1) * ctl.writeInterval - (time_ - ctl.startTime));
+        const double nSteps = timeToNextWrite / deltaT_;
+        if (nSteps < (double)INT32_MAX) {
+            const int nStepsToNextWrite = int(std::max(nSteps, 1.0) + 0.99);
+            const double newDeltaT = timeToNextWrite / nStepsToNextWrite;
+            if (newDeltaT >= deltaT_) deltaT_ = std::min(newDeltaT, 2.0 * deltaT_);
+            else deltaT_ = std::max(newDeltaT, 0.2 * deltaT_);
+        }
+    }
+}
+
+// heatSourceModel::updateDimensions (heatSourceModel.C:123-219)
+void ThermalCase::updateDimensions(heatSourceModel& hs)
+{
+    if (!hs.transient) return;
+    const double* pos = hs.beam.position();
+    const double searchRadius = std::max(hs.staticDimensions[0], hs.staticDimensions[1]);
+    haloExchange(T);
+    // columns that can hold a crossing within the search radius (one extra cell each way)
+    BoxRange cols;
+    const double rx = searchRadius + 2.0 * geo.dx, ry = searchRadius + 2.0 * geo.dy;
+    cols.i0 = std::min(std::max((int)std::floor((pos[0] - rx - geo.ox) / geo.dx), 0), dims.nx);
+    cols.i1 = std::min(std::max((int)std::floor((pos[0] + rx - geo.ox) / geo.dx) + 1, 0), dims.nx);
+    cols.j0 = std::min(std::max((int)std::floor((pos[1] - ry - geo.oy) / geo.dy), 0), dims.ny);
+    cols.j1 = std::min(std::max((int)std::floor((pos[1] + ry - geo.oy) / geo.dy) + 1, 0), dims.ny);
+    cols.k0 = 0; cols.k1 = dims.nz;
+    launch_isotherm_depth(ctx, dims, geo, cols, T, hs.spec.isoValue, pos, searchRadius, hs.staticDimensions[2], rankBelow >= 0,
+                          rankAbove >= 0, red, R_DEPTH);
+    ctx->allreduceMax(red.result + R_DEPTH, 1);
+    d2h(h_red + R_DEPTH, red.result + R_DEPTH, 1, ctx->stream);
+    ctx->sync();
+    hs.dimensions[0] = hs.staticDimensions[0]; hs.dimensions[1] = hs.staticDimensions[1]; hs.dimensions[2] = h_red[R_DEPTH];
+}
+
+// heatSourceModel::qDot() for the beam's current position/power, accumulated as movingHeatSourceModel::update does
+void ThermalCase::qDotOnce(heatSourceModel& hs, double* target, double dt, double sumDt, bool directMean)
+{
+    const double power = hs.beam.power();
+    if (!(power > kSmall)) return;
+    const double aspectRatio = hs.dimensions[2] / std::min(hs.dimensions[0], hs.dimensions[1]);
+    const double absorbedPower = hs.eta(aspectRatio) * power;
+    const double V0 = hs.V0();
+    const ShapeParams sp = hs.shapeParams();
+    const BoxRange box = beam_box(dims, geo, sp.pos, sp.dims);
+    const size_t nb = (size_t)std::max(box.i1 - box.i0, 0) * std::max(box.j1 - box.j0, 0) * std::max(box.k1 - box.k0, 0);
+    if (nb + 1 > wbufCap) { dev_free(wbuf); wbufCap = std::max<size_t>(2 * nb + 1, 4096); wbuf = dev_alloc<double>(wbufCap); }
+    launch_qdot_weights(ctx, dims, geo, sp, box, wbuf, red, R_SUMW);
+    ctx->allreduceSum(red.result + R_SUMW, 1);
+    launch_qdot_apply(ctx, dims, box, wbuf, target, absorbedPower, V0, red.result + R_SUMW, dt, sumDt, directMean ? 1 : 0,
+                      red.result + R_VOLUME);
+}
+
+// movingHeatSourceModel::update (movingHeatSourceModel.C:100-150)
+void launch_qdoti_finish(Ctx* ctx, const BlockDims& d, const BoxRange& box, double* qDoti, double* qDot, double sumDt);
+void ThermalCase::updateSources()
+{
+    const size_t n = (size_t)dims.nCells();
+    B200_CUDA(cudaMemsetAsync(qDot, 0, n * sizeof(double), ctx->stream));
+    for (auto& hs : sources) {
+        if (!hs.beam.activePath(time_)) continue;
+        updateDimensions(hs);
+        double pathTime = time_;
+        const double nextTime = pathTime + deltaT_;
+        const double beam_dt = hs.beam.deltaT();
+        const bool single = !(beam_dt < (nextTime - pathTime));       // the loop below runs exactly once
+        if (!single && !qDoti) qDoti = allocField();
+        double sumWeights = 0.0;
+        BoxRange uni{INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+        while ((nextTime - pathTime) > kSmall) {
+            const double dt = std::min(beam_dt, std::max(0.0, nextTime - pathTime));
+            pathTime += dt;
+            hs.beam.move(pathTime);
+            if (single) qDotOnce(hs, qDot, dt, dt, true);
+            else {
+                qDotOnce(hs, qDoti, dt, 0.0, false);
+                const ShapeParams sp = hs.shapeParams();
+                const BoxRange b = beam_box(dims, geo, sp.pos, sp.dims);
+                uni.i0 = std::min(uni.i0, b.i0); uni.i1 = std::max(uni.i1, b.i1); uni.j0 = std::min(uni.j0, b.j0);
+                uni.j1 = std::max(uni.j1, b.j1); uni.k0 = std::min(uni.k0, b.k0); uni.k1 = std::max(uni.k1, b.k1);
+            }
+            sumWeights += dt;
+        }
+        if (!single && uni.i1 > uni.i0 && uni.j1 > uni.j0 && uni.k1 > uni.k0) launch_qdoti_finish(ctx, dims, uni, qDoti, qDot, sumWeights);
+    }
+}
+
+// mixedTemperature::updateCoeffs for every mixed side whose patch is not `updated`, plus (implicit form)
+// the laplacian boundary coefficients of all sides
+void ThermalCase::updateCoeffsT()
+{
+    for (int sd = 0; sd < 6; sd++) {
+        SideInfo& si = sides[sd];
+        if (si.type != B200_BC_MIXED_TEMPERATURE || si.patch < 0 || patchUpdated[si.patch]) continue;
+        k_side_coeffs<<<flat_grid(ctx, si.n), BLK, 0, ctx->stream>>>(dims, geo, sd, si.type, si.value, si.h, si.emissivity, si.Tinf, kappa,
+                                                                     rKappa, si.valueFraction, si.Tb, si.intCoeff, si.bouCoeff, 1, 0, si.n);
+        B200_LAUNCH_CHECK();
+    }
+    for (size_t p = 0; p < patches.size(); p++) patchUpdated[p] = true;
+}
+
+// T.correctBoundaryConditions(): evaluate() calls updateCoeffs() when the patch is not updated, then resets the flag
+void ThermalCase::evaluateT()
+{
+    updateCoeffsT();
+    for (int sd = 0; sd < 6; sd++) {
+        SideInfo& si = sides[sd];
+        if (si.type != B200_BC_MIXED_TEMPERATURE) continue;     // fixedValue faces are constant, zeroGradient unused
+        k_side_evaluate<<<flat_grid(ctx, si.n), BLK, 0, ctx->stream>>>(dims, sd, si.type, si.value, si.Tinf, T, si.valueFraction, si.Tb,
+                                                                       sd <= B200_XMAX ? geo.bcx : sd <= B200_YMAX ? geo.bcy : geo.bcz, si.n);
+        B200_LAUNCH_CHECK();
+    }
+    for (size_t p = 0; p < patches.size(); p++) patchUpdated[p] = false;
+}
+
+// thermoScheme.H:17-39
+void ThermalCase::assembleBase(bool explicitSolve, double rDeltaT)
+{
+    cudaStream_t s = ctx->stream;
+    updateCoeffsT();                   // fvScalarMatrix TEqn(T, dimPower) -> T.boundaryFieldRef().updateCoeffs()
+    const int grid = cells_grid(ctx, dims);
+    if (!explicitSolve) {
+        for (int sd = 0; sd < 6; sd++) {
+            SideInfo& si = sides[sd];
+            k_side_coeffs<<<flat_grid(ctx, si.n), BLK, 0, s>>>(dims, geo, sd, si.type, si.value, si.h, si.emissivity, si.Tinf, kappa, rKappa,
+                                                               si.valueFraction, si.Tb, si.intCoeff, si.bouCoeff, 0, 1, si.n);
+            B200_LAUNCH_CHECK();
+        }
+        k_faces<false><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK();
+        k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho); B200_LAUNCH_CHECK();
+    } else {
+        haloExchange(T);
+        k_faces<true><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK();
+        k_assemble_explicit<<<grid, BLK, 0, s>>>(dims, geo, sidesDev, Cp, Told, T, qDot, upper, rKappa, diag0, source0, rDeltaT, mat.rho);
+        B200_LAUNCH_CHECK();
+    }
+}
+
+// One pass of the time loop body (additiveFoam.C:66-95)
+void ThermalCase::step(b200_step_report* rep)
+{
+    cudaStream_t s = ctx->stream;
+    const size_t n = (size_t)dims.nCells();
+    double alphaCoMax, diMax, minAlpha1;
+    updatePropertiesAndNumbers(alphaCoMax, diMax, minAlpha1);          // :68 and the reductions of :72
+    setDeltaT(alphaCoMax, diMax);                                      // :72
+    updateSources();                                                   // :74
+    // runTime++ (:76)
+    B200_CUDA(cudaMemcpyAsync(Told, T, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    time_ += deltaT_; timeIndex++;
+    if (ctl.writeInterval > 0) {
+        const int wi = int(((time_ - ctl.startTime) + 0.5 * deltaT_) / ctl.writeInterval);
+        if (wi > writeTimeIndex) writeTimeIndex = wi;
+    }
+    // solutionControls.H
+    k_power<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, qDot, geo.V, red); B200_LAUNCH_CHECK();
+    ctx->allreduceSum(red.result + R_POWER, 1);
+    d2h(h_red + R_POWER, red.result + R_POWER, 1, s);
+    ctx->sync();
+    const double totalPower = h_red[R_POWER];
+    double nThermoCorr = ctl.nThermoCorrectors;
+    const bool beamOn = totalPower > kSmall;
+    const bool fluidInDomain = (1 - minAlpha1) > kSmall;
+    if (!(beamOn || fluidInDomain)) nThermoCorr = 1;
+    bool explicitSolve = ctl.explicitSolve != 0;
+    if (explicitSolve) explicitSolve = diMax * deltaT_ < 1.0;
+    // thermo/TEqn.H
+    const double rDeltaT = 1.0 / deltaT_;
+    assembleBase(explicitSolve, rDeltaT);
+    CorrectorArgs ca;
+    ca.alpha1old = alpha1old; ca.diag0 = diag0; ca.source0 = source0; ca.T = T; ca.alpha1 = alpha1; ca.dFdT = dFdT; ca.T0 = T0;
+    ca.diag = diag; ca.source = source; ca.thermo = d_thermo; ca.nThermo = mat.nThermo; ca.Tliq = Tliq; ca.Tsol = Tsol;
+    ca.thermoTol = ctl.thermoTolerance; ca.Tmax = ctl.Tmax > 0 ? ctl.Tmax : kVGreat; ca.rDeltaT = rDeltaT; ca.rDeltaTEuler = rDeltaT;
+    ca.rho = mat.rho; ca.Lf = mat.Lf;
+    const size_t shm = 2 * (size_t)mat.nThermo * sizeof(double);
+    const int grid = cells_grid(ctx, dims);
+    SolveControls sc;
+    sc.solver = ctl.solver; sc.precond = ctl.preconditioner; sc.tolerance = ctl.tolerance; sc.relTol = ctl.relTol;
+    sc.minIter = ctl.minIter; sc.maxIter = ctl.maxIter;
+    MatrixView A; A.diag = diag; A.upper = upper; A.lower = upper; A.bouCoeffs = bouPtrs;
+    SolvePerf perf;
+    int nCorrDone = 0, iterSum = 0;
+    double residual = 0;
+    for (int tCorr = 0; tCorr < nThermoCorr; tCorr++) {
+        if (explicitSolve) {
+            k_corrector<true><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK();
+            perf = SolvePerf(); perf.converged = 1;
+        } else {
+            k_corrector<false><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK();
+            perf = ldu->solve(A, source, T, sc);
+            iterSum += perf.nIterations;
+            k_alpha_update<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, T, dFdT, T0, alpha1, red); B200_LAUNCH_CHECK();
+        }
+        evaluateT();                                                   // T.correctBoundaryConditions()
+        ctx->allreduceMax(red.result + R_RESID, 1);
+        d2h(h_red + R_RESID, red.result + R_RESID, 1, s);
+        ctx->sync();
+        residual = h_red[R_RESID];
+        nCorrDone = tCorr + 1;
+        if (residual < ctl.thermoTolerance && tCorr > 0) break;
+    }
+    if (rep) {
+        rep->time = time_; rep->deltaT = deltaT_; rep->alphaCoNum = alphaCoNum; rep->DiNum = DiNum; rep->totalPower = totalPower;
+        rep->explicitStep = explicitSolve ? 1 : 0; rep->nThermoCorr = nCorrDone; rep->thermoResidual = residual;
+        rep->nSolveIterations = iterSum; rep->lastSolveIterations = perf.nIterations;
+        rep->lastInitialResidual = perf.initialResidual; rep->lastFinalResidual = perf.finalResidual;
+    }
+}
+
+// heatSourceModel::qDot() on its own (B2 of the drop-in boundary)
+void beam_qdot_standalone(Ctx* ctx, const b200_block_mesh& bm, const b200_beam& beam, const double position[3], const double dimensions[3],
+                          double power, double* qDotOut, double* sumWeights, double* volumeUsed, double* absorbedPowerOut)
+{
+    BlockDims d; d.nx = bm.nx; d.ny = bm.ny; d.nz = bm.nz;
+    Geom g{};
+    g.ox = bm.min[0]; g.oy = bm.min[1]; g.oz = bm.min[2];
+    g.dx = (bm.max[0] - bm.min[0]) / bm.nx; g.dy = (bm.max[1] - bm.min[1]) / bm.ny; g.dz = (bm.max[2] - bm.min[2]) / bm.nz;
+    g.V = g.dx * g.dy * g.dz; g.k0 = 0;
+    const size_t n = (size_t)d.nCells();
+    b200_beam spec = beam; spec.nSegments = 0; spec.path = nullptr;
+    heatSourceModel hs(spec, 0.0, 0.0);
+    for (int q = 0; q < 3; q++) hs.dimensions[q] = dimensions[q];
+    if (sumWeights) *sumWeights = 0;
+    if (volumeUsed) *volumeUsed = 0;
+    if (absorbedPowerOut) *absorbedPowerOut = 0;
+    double* q = dev_alloc<double>(n);
+    B200_CUDA(cudaMemsetAsync(q, 0, n * sizeof(double), ctx->stream));
+    RedWork red;
+    red.partials = dev_alloc<double>((size_t)R_NSLOTS * RED_MAX_BLOCKS);
+    red.ticket = dev_alloc<unsigned>(1); red.result = dev_alloc<double>(R_NSLOTS);
+    B200_CUDA(cudaMemsetAsync(red.ticket, 0, sizeof(unsigned), ctx->stream));
+    B200_CUDA(cudaMemsetAsync(red.result, 0, sizeof(double) * R_NSLOTS, ctx->stream));
+    double* wb = nullptr;
+    if (power > kSmall) {
+        const double aspectRatio = hs.dimensions[2] / std::min(hs.dimensions[0], hs.dimensions[1]);
+        const double absorbed = hs.eta(aspectRatio) * power;
+        const double V0 = hs.V0();
+        ShapeParams sp = hs.shapeParams();
+        for (int c = 0; c < 3; c++) sp.pos[c] = position[c];
+        const BoxRange box = beam_box(d, g, sp.pos, sp.dims);
+        const size_t nb = (size_t)std::max(box.i1 - box.i0, 0) * std::max(box.j1 - box.j0, 0) * std::max(box.k1 - box.k0, 0);
+        wb = dev_alloc<double>(nb + 1);
+        launch_qdot_weights(ctx, d, g, sp, box, wb, red, R_SUMW);
+        launch_qdot_apply(ctx, d, box, wb, q, absorbed, V0, red.result + R_SUMW, 0.0, 0.0, 2, red.result + R_VOLUME);
+        double h[R_NSLOTS];
+        d2h(h, red.result, R_NSLOTS, ctx->stream);
+        ctx->sync();
+        if (sumWeights) *sumWeights = h[R_SUMW];
+        if (volumeUsed) *volumeUsed = h[R_VOLUME];
+        if (absorbedPowerOut) *absorbedPowerOut = absorbed;
+    }
+    d2h(qDotOut, q, n, ctx->stream);
+    ctx->sync();
+    dev_free(q); dev_free(wb); dev_free(red.partials); dev_free(red.ticket); dev_free(red.result);
+}
+
+} // namespace b200

@@ -1,0 +1,121 @@
+// GPU-resident thermal step on one blockMesh hex block (one z-slab of it per rank).
+// Replaces the body of the reference's time loop, applications/solvers/additiveFoam/additiveFoam.C:66-95:
+//   updateProperties.H, setDeltaT.H, movingHeatSourceModel::update(), solutionControls.H, thermo/TEqn.H
+//   (thermoScheme.H + thermoSource.H) and, underneath, OpenFOAM-10's Euler ddt / Gauss-harmonic laplacian
+//   assembly, boundary-coefficient folding (fvMatrix::solveSegregated) and lduMatrix solvers.
+// Fields stay on the device for the whole run; per step the host sees a handful of scalars.
+#pragma once
+#include "../../include/additivefoam_b200.h"
+#include "ctx.cuh"
+#include "ldu.cuh"
+#include "beam.cuh"
+#include <vector>
+#include <memory>
+
+namespace b200 {
+
+struct Geom {
+    double ox, oy, oz, dx, dy, dz, V;
+    double sfx, sfy, sfz;       // |Sf| of x-, y-, z-normal faces
+    double dcx, dcy, dcz;       // deltaCoeffs of internal faces
+    double bcx, bcy, bcz;       // deltaCoeffs of boundary faces (cell centre to face)
+    int k0;                     // global k index of local plane 0
+};
+
+constexpr int SIDE_PROCESSOR = 3;     // extends B200_BC_*
+
+struct SideInfo {
+    int type = B200_BC_ZERO_GRADIENT; // B200_BC_* or SIDE_PROCESSOR
+    int patch = -1;
+    double value = 0, h = 0, emissivity = 0, Tinf = 0;
+    int n = 0;                        // faces on this side (local)
+    double *valueFraction = nullptr, *Tb = nullptr, *intCoeff = nullptr, *bouCoeff = nullptr;   // device, size n
+};
+
+// what the cell kernels need to know about the six sides, by value
+struct SidesDev {
+    int type[6];
+    int order[6];                     // sides in summation order (patch order, then processor sides)
+    int nOrder;
+    const double* intCoeff[6];
+    const double* bouCoeff[6];
+    const double* valueFraction[6];
+    const double* Tb[6];
+    double Tinf[6];
+};
+
+struct BoxRange { int i0, i1, j0, j1, k0, k1; };   // half-open local index box
+
+class ThermalCase {
+public:
+    ThermalCase(Ctx* ctx, const b200_case_desc& desc);
+    ~ThermalCase();
+    bool running() const { return time_ < (ctl.endTime - 0.5 * deltaT_); }
+    void step(b200_step_report* rep);
+    int64_t nLocal() const { return dims.nCells(); }
+    int64_t nGlobal() const { return (int64_t)dims.nx * dims.ny * nzGlobal; }
+    void getField(int field, double* out);
+    void setField(int field, const double* in);
+
+    Ctx* ctx;
+private:
+    // description (owned copies)
+    b200_controls ctl{};
+    b200_material mat{};
+    std::vector<double> thermoT, thermoA;
+    double Tliq = 0, Tsol = 0, Tinitial = 300;
+    std::vector<b200_patch> patches;
+    std::vector<heatSourceModel> sources;
+    BlockDims dims; int nzGlobal = 0; Geom geo{};
+    int rankBelow = -1, rankAbove = -1;
+    SideInfo sides[6];
+    SidesDev sidesDev{};
+    std::vector<bool> patchUpdated;
+    // time
+    double time_ = 0, deltaT_ = 0;
+    int timeIndex = 0, writeTimeIndex = 0;
+    double alphaCoNum = 0, DiNum = 0;
+    // fields (device, each with one ghost plane either side; pointers address cell 0)
+    size_t plane = 0, padded = 0;
+    std::vector<double*> allocs;
+    double *T = nullptr, *Told = nullptr, *alpha1 = nullptr, *alpha1old = nullptr, *alpha3 = nullptr, *kappa = nullptr,
+           *rKappa = nullptr, *Cp = nullptr, *qDot = nullptr, *qDoti = nullptr, *dFdT = nullptr, *T0 = nullptr,
+           *diag0 = nullptr, *source0 = nullptr, *diag = nullptr, *source = nullptr, *upper = nullptr, *wbuf = nullptr;
+    size_t wbufCap = 0;
+    double* d_thermo = nullptr;          // thermoPath table on the device: x then y
+    std::unique_ptr<Ldu> ldu;
+    RedWork red{};
+    double* h_red = nullptr;             // pinned mirror of red.result
+    const double* bouPtrs[2] = {nullptr, nullptr};
+
+    double* field(int f);
+    double* allocField();
+    void haloExchange(double* f);
+    void updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1);
+    void setDeltaT(double alphaCoMax, double diMax);
+    void updateSources();
+    void qDotOnce(heatSourceModel& hs, double* target, double dt, double sumDt, bool accumulate);
+    void updateDimensions(heatSourceModel& hs);
+    void updateCoeffsT();
+    void evaluateT();
+    void assembleBase(bool explicitSolve, double rDeltaT);
+    void readReductions(int n);
+    friend void beam_qdot_standalone(Ctx*, const b200_block_mesh&, const b200_beam&, const double*, const double*, double, double*,
+                                     double*, double*, double*);
+};
+
+void beam_qdot_standalone(Ctx* ctx, const b200_block_mesh& mesh, const b200_beam& beam, const double position[3],
+                          const double dimensions[3], double power, double* qDot, double* sumWeights, double* volumeUsed,
+                          double* absorbedPower);
+
+// device entry points of beam.cu
+void launch_qdot_weights(Ctx* ctx, const BlockDims& d, const Geom& g, const ShapeParams& sp, const BoxRange& box, double* wbuf,
+                         RedWork red, int slot);
+void launch_qdot_apply(Ctx* ctx, const BlockDims& d, const BoxRange& box, const double* wbuf, double* target, double absorbedPower,
+                       double V0, const double* sumWeights, double dt, double sumDt, int directMean, double* volumeOut);
+void launch_isotherm_depth(Ctx* ctx, const BlockDims& d, const Geom& g, const BoxRange& cols, const double* T, double isoValue,
+                           const double pos[3], double searchRadius, double staticDepth, bool ghostBelow, bool ghostAbove,
+                           RedWork red, int slot);
+BoxRange beam_box(const BlockDims& d, const Geom& g, const double pos[3], const double dims[3]);
+
+} // namespace b200

@@ -1,0 +1,240 @@
+"""ctypes binding of the CUDA library (``libadditivefoam_b200.so``) -- the product path.
+
+No fallback: if the shared library is missing or no CUDA device is present, loading / context
+creation raises.  The classes mirror the reference interfaces the library replaces:
+
+* :class:`LduSolver`  -- ``Foam::lduMatrix::solver`` ([UPSTREAM OpenFOAM-10]; constructed from the LDU
+  addressing, ``solve(psi, source)`` per call; ``solver``/``preconditioner``/``tolerance``/``relTol``/
+  ``minIter``/``maxIter`` as in ``system/fvSolution``, tutorials/AMB2018-02-B/system/fvSolution:34-42)
+* :func:`beam_qdot`   -- ``heatSourceModel::qDot()`` (movingHeatSource/heatSourceModels/heatSourceModel/heatSourceModel.C:221-371)
+* :class:`Case`       -- the time-loop body of applications/solvers/additiveFoam/additiveFoam.C:66-95
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, cases
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libadditivefoam_b200.so")
+
+dp, ip = abi.c_double_p, abi.c_int32_p
+
+#: every symbol include/additivefoam_b200.h declares
+SYMBOLS = [
+    "b200_last_error", "b200_abi_version", "b200_nccl_unique_id", "b200_ctx_create", "b200_ctx_destroy",
+    "b200_ctx_synchronize", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
+    "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
+    "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_kernel_launches",
+    "b200_scan_path_parse",
+]
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the CUDA library; raises if it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise B200Error(f"{SO_PATH} is missing: build it with additivefoam_b200/csrc/Makefile; there is no CPU fallback")
+    L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    L.b200_last_error.restype = C.c_char_p
+    vp = C.c_void_p
+    L.b200_nccl_unique_id.argtypes = [vp]
+    L.b200_ctx_create.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.b200_ctx_destroy.argtypes = [vp]
+    L.b200_ctx_synchronize.argtypes = [vp]
+    L.b200_ldu_create.argtypes = [vp, C.c_int32, C.c_int32, ip, ip, C.c_int32, ip, ip, C.POINTER(ip), C.POINTER(vp)]
+    L.b200_ldu_destroy.argtypes = [vp]
+    L.b200_ldu_set_block.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
+    L.b200_ldu_solve.argtypes = [vp, C.c_int32, C.c_int32, dp, dp, dp, C.POINTER(dp), dp, dp, C.c_double, C.c_double,
+                                 C.c_int32, C.c_int32, C.POINTER(abi.SolverPerf)]
+    L.b200_ldu_solve_dev.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_double, C.c_double,
+                                     C.c_int32, C.c_int32, C.POINTER(abi.SolverPerf)]
+    L.b200_ldu_amul.argtypes = [vp, dp, dp, dp, C.POINTER(dp), dp, dp]
+    L.b200_ldu_amul_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    L.b200_ldu_precondition.argtypes = [vp, C.c_int32, dp, dp, dp, dp, dp]
+    L.b200_ldu_levels.argtypes = [vp, ip, ip]
+    L.b200_beam_qdot.argtypes = [vp, C.POINTER(abi.BlockMesh), C.POINTER(abi.Beam), dp, dp, C.c_double, dp, dp, dp, dp]
+    L.b200_case_create.argtypes = [vp, C.POINTER(abi.CaseDesc), C.POINTER(vp)]
+    L.b200_case_destroy.argtypes = [vp]
+    L.b200_case_running.argtypes = [vp]
+    L.b200_case_step.argtypes = [vp, C.POINTER(abi.StepReport)]
+    L.b200_case_n_cells.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.b200_case_get_field.argtypes = [vp, C.c_int32, dp]
+    L.b200_case_set_field.argtypes = [vp, C.c_int32, dp]
+    L.b200_case_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
+    L.b200_scan_path_parse.argtypes = [C.c_char_p, dp, C.c_int32]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200Error(load().b200_last_error().decode())
+
+
+def _P(a):
+    if a is None:
+        return None
+    if a.dtype == np.float64:
+        return a.ctypes.data_as(dp)
+    if a.dtype == np.int32:
+        return a.ctypes.data_as(ip)
+    raise TypeError(a.dtype)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def nccl_unique_id():
+    buf = (C.c_char * 128)()
+    _check(load().b200_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class Context:
+    """One per process = one GPU = one subdomain (the reference's MPI rank)."""
+
+    def __init__(self, device=0, unique_id=None, rank=0, nranks=1):
+        self.L = load()
+        self.h = C.c_void_p()
+        uid = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        _check(self.L.b200_ctx_create(device, uid, rank, nranks, C.byref(self.h)))
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    def synchronize(self):
+        _check(self.L.b200_ctx_synchronize(self.h))
+
+    def kernel_launches(self):
+        n = C.c_int64()
+        self.L.b200_case_kernel_launches(None, C.byref(n))
+        return n.value
+
+    def close(self):
+        if self.h:
+            self.L.b200_ctx_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class LduSolver:
+    """``lduMatrix::solver`` on the GPU: addressing at construction, coefficients per ``solve``."""
+
+    def __init__(self, ctx, lower, upper, n_cells, block=None, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC,
+                 tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000):
+        self.ctx, self.L = ctx, ctx.L
+        self.lower = np.ascontiguousarray(lower, dtype=np.int32)
+        self.upper = np.ascontiguousarray(upper, dtype=np.int32)
+        self.n, self.nf = int(n_cells), len(self.lower)
+        self.h = C.c_void_p()
+        _check(self.L.b200_ldu_create(ctx.h, self.n, self.nf, _P(self.lower), _P(self.upper), 0, None, None, None, C.byref(self.h)))
+        if block is not None:
+            _check(self.L.b200_ldu_set_block(self.h, *block))
+        self.controls = dict(solver=solver, preconditioner=preconditioner, tolerance=tolerance, relTol=relTol,
+                             minIter=minIter, maxIter=maxIter)
+
+    def solve(self, psi, source, diag, upper, lower=None, **kw):
+        c = dict(self.controls)
+        c.update(kw)
+        psi = _f64(psi).copy()
+        perf = abi.SolverPerf()
+        diag, upper, source = _f64(diag), _f64(upper), _f64(source)
+        lower = None if lower is None else _f64(lower)
+        _check(self.L.b200_ldu_solve(self.h, c["solver"], c["preconditioner"], _P(diag), _P(upper), _P(lower), None, _P(source),
+                                     _P(psi), c["tolerance"], c["relTol"], c["minIter"], c["maxIter"], C.byref(perf)))
+        return psi, perf
+
+    def amul(self, psi, diag, upper, lower=None):
+        psi, diag, upper = _f64(psi), _f64(diag), _f64(upper)
+        lower = None if lower is None else _f64(lower)
+        out = np.empty(self.n)
+        _check(self.L.b200_ldu_amul(self.h, _P(diag), _P(upper), _P(lower), None, _P(psi), _P(out)))
+        return out
+
+    def precondition(self, kind, rA, diag, upper, lower=None):
+        rA, diag, upper = _f64(rA), _f64(diag), _f64(upper)
+        lower = None if lower is None else _f64(lower)
+        out = np.empty(self.n)
+        _check(self.L.b200_ldu_precondition(self.h, kind, _P(diag), _P(upper), _P(lower), _P(rA), _P(out)))
+        return out
+
+    def levels(self):
+        lv = np.empty(self.n, dtype=np.int32)
+        nl = C.c_int32()
+        _check(self.L.b200_ldu_levels(self.h, _P(lv), C.byref(nl)))
+        return lv, nl.value
+
+    def close(self):
+        if self.h:
+            self.L.b200_ldu_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def beam_qdot(ctx, mesh, beam, position, dimensions, power):
+    """heatSourceModel::qDot() for one beam state; returns (qDot[nCells], sumWeights, volumeUsed, absorbedPower)."""
+    L = ctx.L
+    bm = abi.BlockMesh()
+    bm.nx, bm.ny, bm.nz = mesh["n"]
+    for q in range(3):
+        bm.min[q], bm.max[q] = mesh["min"][q], mesh["max"][q]
+    b = cases.make_beam(beam)
+    n = bm.nx * bm.ny * bm.nz
+    out = np.empty(n)
+    pos, dims = _f64(position), _f64(dimensions)
+    sw, vol, ap = C.c_double(), C.c_double(), C.c_double()
+    _check(L.b200_beam_qdot(ctx.h, C.byref(bm), C.byref(b), _P(pos), _P(dims), power, _P(out),
+                            C.cast(C.byref(sw), dp), C.cast(C.byref(vol), dp), C.cast(C.byref(ap), dp)))
+    return out, sw.value, vol.value, ap.value
+
+
+class Case:
+    """GPU-resident thermal case; ``step()`` is one pass of additiveFoam's ``while (runTime.run())`` body."""
+
+    def __init__(self, ctx, case):
+        self.ctx, self.L = ctx, ctx.L
+        self.built = cases.BuiltCase(case)
+        self.h = C.c_void_p()
+        _check(self.L.b200_case_create(ctx.h, C.byref(self.built.desc), C.byref(self.h)))
+        nl, ng = C.c_int64(), C.c_int64()
+        _check(self.L.b200_case_n_cells(self.h, C.byref(nl), C.byref(ng)))
+        self.n_local, self.n_global = nl.value, ng.value
+
+    def running(self):
+        return bool(self.L.b200_case_running(self.h))
+
+    def step(self):
+        rep = abi.StepReport()
+        _check(self.L.b200_case_step(self.h, C.byref(rep)))
+        return rep
+
+    def field(self, f):
+        out = np.empty(self.n_local)
+        _check(self.L.b200_case_get_field(self.h, f, _P(out)))
+        return out
+
+    def set_field(self, f, a):
+        a = _f64(a)
+        assert a.size == self.n_local
+        _check(self.L.b200_case_set_field(self.h, f, _P(a)))
+
+    def close(self):
+        if self.h:
+            self.L.b200_case_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+def scan_path_parse(text, max_segments=4096):
+    out = np.empty(6 * max_segments)
+    n = load().b200_scan_path_parse(text.encode(), _P(out), max_segments)
+    if n < 0:
+        raise B200Error("scan path has more segments than max_segments")
+    return out[: 6 * n].reshape(n, 6).copy()
