@@ -55,6 +55,41 @@ int b200_ctx_synchronize(b200_ctx* ctx)
     B200_CATCH
 }
 
+int b200_ctx_mark(b200_ctx* ctx, int i)
+{
+    B200_TRY
+    B200_CHECK(i >= 0 && i < 4, "mark index");
+    B200_CUDA(cudaEventRecord(ctx->p->marks[i], ctx->p->stream));
+    B200_CATCH
+}
+int b200_ctx_elapsed_ms(b200_ctx* ctx, int i, int j, double* ms)
+{
+    B200_TRY
+    B200_CHECK(i >= 0 && i < 4 && j >= 0 && j < 4, "mark index");
+    B200_CUDA(cudaEventSynchronize(ctx->p->marks[j]));
+    float t = 0;
+    B200_CUDA(cudaEventElapsedTime(&t, ctx->p->marks[i], ctx->p->marks[j]));
+    *ms = t;
+    B200_CATCH
+}
+int b200_profile_enable(b200_ctx* ctx, int on)
+{
+    B200_TRY
+    ctx->p->profRead(nullptr, nullptr);
+    ctx->p->profOn = on != 0;
+    B200_CATCH
+}
+int b200_profile_groups(void) { return PC_NCAT; }
+const char* b200_profile_name(int group) { return prof_name(group); }
+int b200_profile_read(b200_ctx* ctx, double* ms, int64_t* counts, int n)
+{
+    B200_TRY
+    double m[PC_NCAT]; int64_t c[PC_NCAT];
+    ctx->p->profRead(m, c);
+    for (int i = 0; i < n && i < PC_NCAT; i++) { ms[i] = m[i]; counts[i] = c[i]; }
+    B200_CATCH
+}
+
 int b200_ldu_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, const int32_t* lower, const int32_t* upper, int32_t nInterfaces,
                     const int32_t* ifaceNeighbRank, const int32_t* ifaceSize, const int32_t* const* ifaceFaceCells, b200_ldu** out)
 {

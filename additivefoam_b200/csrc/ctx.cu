@@ -16,6 +16,7 @@ Ctx::Ctx(int dev, const void* uniqueId, int rank_, int nranks_) : device(dev), r
     B200_CUDA(cudaGetDeviceProperties(&prop, dev));
     smCount = prop.multiProcessorCount;
     B200_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    for (auto& e : marks) B200_CUDA(cudaEventCreate(&e));
     if (nranks > 1) {
         B200_CHECK(uniqueId != nullptr, "nccl unique id required for nranks > 1");
         ncclUniqueId id;
@@ -24,8 +25,38 @@ Ctx::Ctx(int dev, const void* uniqueId, int rank_, int nranks_) : device(dev), r
     }
 }
 
+const char* prof_name(int cat)
+{
+    static const char* names[PC_NCAT] = {"amul", "sweep_fwd", "sweep_bwd", "factor", "vector", "normfactor", "ctrl", "props", "dinum",
+                                         "faces", "assemble", "corrector", "alpha", "boundary", "qdot", "copy", "comm"};
+    return cat >= 0 && cat < PC_NCAT ? names[cat] : "?";
+}
+
+cudaEvent_t Ctx::profEvent()
+{
+    if (!profPool.empty()) { cudaEvent_t e = profPool.back(); profPool.pop_back(); return e; }
+    cudaEvent_t e;
+    B200_CUDA(cudaEventCreate(&e));
+    return e;
+}
+
+void Ctx::profRead(double* ms, int64_t* counts)
+{
+    sync();
+    for (auto& r : profRecs) {
+        float t = 0;
+        if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { profMs[r.cat] += t; profCount[r.cat]++; }
+        profPool.push_back(r.a); profPool.push_back(r.b);
+    }
+    profRecs.clear();
+    for (int i = 0; i < PC_NCAT; i++) { if (ms) ms[i] = profMs[i]; if (counts) counts[i] = profCount[i]; profMs[i] = 0; profCount[i] = 0; }
+}
+
 Ctx::~Ctx()
 {
+    for (auto& r : profRecs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : profPool) cudaEventDestroy(e);
+    for (auto e : marks) if (e) cudaEventDestroy(e);
     if (comm) ncclCommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
 }

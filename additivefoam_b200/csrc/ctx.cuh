@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include <nccl.h>
+#include <vector>
 
 namespace b200 {
 
@@ -13,8 +14,23 @@ namespace b200 {
                                 __FILE__ + ":" + std::to_string(__LINE__));                      \
     } while (0)
 
+// kernel groups timed by the built-in CUDA-event profiler (bench.py's roofline numbers)
+enum ProfCat { PC_AMUL = 0, PC_SWEEP_FWD, PC_SWEEP_BWD, PC_FACTOR, PC_VECTOR, PC_NORMFACTOR, PC_CTRL, PC_PROPS, PC_DINUM, PC_FACES,
+               PC_ASSEMBLE, PC_CORRECTOR, PC_ALPHA, PC_BOUNDARY, PC_QDOT, PC_COPY, PC_COMM, PC_NCAT };
+const char* prof_name(int cat);
+
 struct Ctx {
     int device = 0, rank = 0, nranks = 1;
+    // profiler: one event pair per instrumented launch group, resolved at read time
+    bool profOn = false;
+    struct ProfRec { int cat; cudaEvent_t a, b; };
+    std::vector<ProfRec> profRecs;
+    std::vector<cudaEvent_t> profPool;
+    double profMs[PC_NCAT] = {0};
+    int64_t profCount[PC_NCAT] = {0};
+    cudaEvent_t marks[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t profEvent();
+    void profRead(double* ms, int64_t* counts);
     int smCount = 148;
     int maxCoopBlocksPerSm = 8;
     cudaStream_t stream = nullptr;
@@ -35,6 +51,18 @@ struct Ctx {
     // plane / buffer exchange with a neighbour rank (either may be null)
     void sendrecv(const double* sendLo, double* recvLo, int rankLo, const double* sendHi, double* recvHi, int rankHi,
                   size_t count);
+};
+
+struct ProfScope {
+    Ctx* c; cudaEvent_t b = nullptr;
+    ProfScope(Ctx* ctx, int cat) : c(ctx)
+    {
+        if (!c->profOn) return;
+        cudaEvent_t a = c->profEvent(); b = c->profEvent();
+        c->profRecs.push_back({cat, a, b});
+        cudaEventRecord(a, c->stream);
+    }
+    ~ProfScope() { if (b) cudaEventRecord(b, c->stream); }
 };
 
 template <class T> inline T* dev_alloc(size_t n)

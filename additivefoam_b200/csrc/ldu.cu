@@ -165,6 +165,7 @@ void Ldu::ensureWork()
 void Ldu::exchange(const double* x)
 {
     if (ctx->nranks <= 1) return;
+    ProfScope ps_(ctx, PC_COMM);
     if (isBlock && (ghostBelow || ghostAbove)) {
         const size_t plane = (size_t)dims.nx * dims.ny;
         double* xw = const_cast<double*>(x);
@@ -187,6 +188,8 @@ void Ldu::exchange(const double* x)
 
 void Ldu::allreduce(int slot0, int n, bool)
 {
+    if (ctx->nranks <= 1) return;
+    ProfScope ps_(ctx, PC_COMM);
     ctx->allreduceSum(red.result + slot0, n);
 }
 
@@ -194,6 +197,7 @@ void Ldu::allreduce(int slot0, int n, bool)
 template <int MODE> static void launch_amul(Ldu& L, const MatrixView& A, const double* x, double* y, const double* aux, const SolveState* st)
 {
     cudaStream_t s = L.ctx->stream;
+    ProfScope ps_(L.ctx, PC_AMUL);
     if (L.isBlock) {
         const double* bb = (L.ghostBelow && A.bouCoeffs) ? A.bouCoeffs[0] : nullptr;
         const double* ba = (L.ghostAbove && A.bouCoeffs) ? A.bouCoeffs[L.ghostBelow ? 1 : 0] : nullptr;
@@ -233,8 +237,8 @@ void Ldu::amulFused(const MatrixView& A, const double* x, double* y, int mode, c
     else if (mode == AM_DOT_YX) { k_dot<<<redBlocks, BLK, 0, s>>>(n, y, x, red, S_DEN, st); B200_LAUNCH_CHECK(); }
     else if (mode == AM_DOT_AUXY) { k_dot<<<redBlocks, BLK, 0, s>>>(n, aux, y, red, S_DEN, st); B200_LAUNCH_CHECK(); }
     else if (mode == AM_TT_TS) {
-        k_dot<<<redBlocks, BLK, 0, s>>>(n, y, y, red, S_TT, st); B200_LAUNCH_CHECK();
-        k_dot<<<redBlocks, BLK, 0, s>>>(n, y, aux, red, S_TS, st); B200_LAUNCH_CHECK();
+        { ProfScope ps_(ctx, PC_VECTOR); k_dot<<<redBlocks, BLK, 0, s>>>(n, y, y, red, S_TT, st); B200_LAUNCH_CHECK(); }
+        { ProfScope ps_(ctx, PC_VECTOR); k_dot<<<redBlocks, BLK, 0, s>>>(n, y, aux, red, S_TS, st); B200_LAUNCH_CHECK(); }
     }
 }
 
@@ -251,6 +255,7 @@ void Ldu::factor(int kind, const MatrixView& A)
     cudaStream_t s = ctx->stream;
     const SolveState* st = d_state;
     if (kind == 0) return;
+    ProfScope ps_(ctx, PC_FACTOR);
     if (kind == 1) {
         k_copy<<<redBlocks, BLK, 0, s>>>((int64_t)nCells, A.diag, rD + ghost, st); B200_LAUNCH_CHECK();
     } else {
@@ -275,24 +280,24 @@ void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* 
     cudaStream_t s = ctx->stream;
     const SolveState* st = d_state;
     double* rd = rD + ghost;
-    if (kind == 0) { k_precond_pointwise<false><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
-    if (kind == 1) { k_precond_pointwise<true><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
+    if (kind == 0) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<false><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
+    if (kind == 1) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<true><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
     const bool dilu = kind == 3;
     const double* nul = nullptr;
     if (isBlock) {
         const int64_t work_ = (int64_t)dims.ny * dims.nz;
-        if (dilu) coop_launch(ctx, k_sweep_block<1, true, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
-        else coop_launch(ctx, k_sweep_block<1, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
-        if (doDot) coop_launch(ctx, k_sweep_block<2, false, true>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st);
-        else coop_launch(ctx, k_sweep_block<2, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+        if (dilu) { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, true, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
+        else { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
+        if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, true>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st); }
+        else { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
     } else {
         const int* ls = d_lvlStart; const int* lc = d_lvlCells; const int* rs = d_rowStart; const int* rm = d_rowMid;
         const int* rc = d_rowCol; const int* rf = d_rowFace;
         const int64_t work_ = maxLevelSize;
-        if (dilu) coop_launch(ctx, k_sweep_general<1, true, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
-        else coop_launch(ctx, k_sweep_general<1, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
-        if (doDot) coop_launch(ctx, k_sweep_general<2, false, true>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st);
-        else coop_launch(ctx, k_sweep_general<2, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st);
+        if (dilu) { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_general<1, true, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
+        else { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_general<1, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
+        if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_general<2, false, true>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st); }
+        else { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_general<2, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
     }
 }
 
@@ -307,6 +312,7 @@ void Ldu::precondition(int kind, const MatrixView& A, const double* rA, double* 
 // ------------------------------------------------------------------ Krylov drivers
 static void ctrl(Ldu& L, int phase)
 {
+    ProfScope ps_(L.ctx, PC_CTRL);
     k_ctrl<<<1, 1, 0, L.ctx->stream>>>(phase, L.d_state, L.red.result, &L.d_state->early);
     B200_LAUNCH_CHECK();
 }
@@ -350,9 +356,11 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
         const int64_t items = (int64_t)((dims.nx + BLK - 1) / BLK) * dims.ny * dims.nz;
         const int grid = (int)std::min<int64_t>(items, ctx->persistentBlocks());
         B200_CHECK(ifaces.empty(), "block addressing with general interfaces: use ghost planes");
+        ProfScope ps_(ctx, PC_NORMFACTOR);
         k_normfactor_block<<<grid, BLK, 0, s>>>(dims, A.diag, A.upper, A.lower, bb, ba, source, wA, rA, red, st);
         B200_LAUNCH_CHECK();
     } else {
+        ProfScope ps_(ctx, PC_NORMFACTOR);
         if (!d_sumA) d_sumA = dev_alloc<double>(n);
         k_sumA_general<<<redBlocks, BLK, 0, s>>>(nCells, d_rowStart, d_rowMid, d_rowFace, A.diag, A.upper, A.lower, d_sumA);
         B200_LAUNCH_CHECK();
@@ -368,7 +376,7 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     allreduce(S_NORM, 2);
     ctrl(*this, C_INIT);
     factor(sc.precond, A);
-    if (!pcg) { k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); }
+    if (!pcg) { { ProfScope ps_(ctx, PC_VECTOR); k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); } }
 
     const int hardMax = std::max(sc.maxIter + 1, sc.minIter);
     int enqueued = 0, chunk = 2;
@@ -378,32 +386,32 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
                 applyPrecond(sc.precond, A, rA, wA, 1, rA);         // wA = M^-1 rA ; wArA
                 allreduce(S_RHO, 1);
                 ctrl(*this, C_PCG_BETA);
-                k_pcg_p<<<redBlocks, BLK, 0, s>>>(n, wA, pA, st); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_pcg_p<<<redBlocks, BLK, 0, s>>>(n, wA, pA, st); B200_LAUNCH_CHECK(); }
                 amulFused(A, pA, qA, AM_DOT_YX, nullptr);           // q = A pA ; wApA
                 allreduce(S_DEN, 1);
                 ctrl(*this, C_PCG_ALPHA);
-                k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, red, st); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, red, st); B200_LAUNCH_CHECK(); }
                 allreduce(S_MAGR, 1);
                 ctrl(*this, C_ITER_END);
             } else {
-                k_dot<<<redBlocks, BLK, 0, s>>>(n, rA0, rA, red, S_RHO, st); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_dot<<<redBlocks, BLK, 0, s>>>(n, rA0, rA, red, S_RHO, st); B200_LAUNCH_CHECK(); }
                 allreduce(S_RHO, 1);
                 ctrl(*this, C_BICG_RHO);
-                k_bicg_p<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, pA, st); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_p<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, pA, st); B200_LAUNCH_CHECK(); }
                 applyPrecond(sc.precond, A, pA, yA, 0, nullptr);
                 amulFused(A, yA, AyA, AM_DOT_AUXY, rA0);            // rA0 . AyA
                 allreduce(S_DEN, 1);
                 ctrl(*this, C_BICG_ALPHA);
-                k_bicg_s<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, sA, red, st); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_s<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, sA, red, st); B200_LAUNCH_CHECK(); }
                 allreduce(S_MAGR, 1);
                 ctrl(*this, C_BICG_SCHECK);
-                k_bicg_early<<<redBlocks, BLK, 0, s>>>(n, yA, psi, st, &d_state->early); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_early<<<redBlocks, BLK, 0, s>>>(n, yA, psi, st, &d_state->early); B200_LAUNCH_CHECK(); }
                 ctrl(*this, C_BICG_EARLY_END);
                 applyPrecond(sc.precond, A, sA, zA, 0, nullptr);
                 amulFused(A, zA, tA, AM_TT_TS, sA);                 // tA.tA, tA.sA
                 allreduce(S_TT, 2);
                 ctrl(*this, C_BICG_OMEGA);
-                k_bicg_update<<<redBlocks, BLK, 0, s>>>(n, yA, zA, sA, tA, psi, rA, red, st); B200_LAUNCH_CHECK();
+                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_update<<<redBlocks, BLK, 0, s>>>(n, yA, zA, sA, tA, psi, rA, red, st); B200_LAUNCH_CHECK(); }
                 allreduce(S_MAGR2, 1);
                 ctrl(*this, C_ITER_END2);
             }

@@ -181,10 +181,13 @@ void ThermalCase::getField(int f, double* out)
     ctx->sync();
 }
 
-void ThermalCase::setField(int f, const double* in)
+void ThermalCase::setField(int fIn, const double* in)
 {
     const size_t n = (size_t)dims.nCells();
+    const bool keepOld = (fIn & 0x100) != 0;     // B200_FIELD_KEEP_OLD: upload only (the host owns the field between steps)
+    const int f = fIn & 0xff;
     h2d(field(f), in, n, ctx->stream);
+    if (keepOld) { ctx->sync(); return; }
     if (f == B200_FIELD_T) {
         B200_CUDA(cudaMemcpyAsync(Told, T, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
         evaluateT();
@@ -196,6 +199,7 @@ void ThermalCase::setField(int f, const double* in)
 void ThermalCase::haloExchange(double* f)
 {
     if (ctx->nranks <= 1) return;
+    ProfScope ps_(ctx, PC_COMM);
     ctx->sendrecv(f, f - plane, rankBelow, f + (size_t)(dims.nz - 1) * plane, f + (size_t)dims.nz * plane, rankAbove, plane);
 }
 
@@ -212,12 +216,14 @@ void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, 
     MatDev m;
     std::memcpy(m.kappa, mat.kappa, sizeof(m.kappa)); std::memcpy(m.Cp, mat.Cp, sizeof(m.Cp));
     m.rho = mat.rho; m.Lf = mat.Lf; m.Tliq = Tliq; m.Tsol = Tsol;
+    { ProfScope ps_(ctx, PC_PROPS);
     k_props<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, m, T, Told, alpha1, alpha3, kappa, rKappa, Cp, 1.0 / deltaT_, deltaT_, red);
-    B200_LAUNCH_CHECK();
+    B200_LAUNCH_CHECK(); }
     haloExchange(kappa);
     haloExchange(rKappa);
+    { ProfScope ps_(ctx, PC_DINUM);
     k_dinum<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, geo, sidesDev, kappa, Cp, mat.rho, red);
-    B200_LAUNCH_CHECK();
+    B200_LAUNCH_CHECK(); }
     if (ctx->nranks > 1) {
         ctx->allreduceMax(red.result + R_ALPHACO, 1);
         ctx->allreduceMin(red.result + R_MINALPHA, 1);
@@ -298,6 +304,7 @@ void launch_qdoti_finish(Ctx* ctx, const BlockDims& d, const BoxRange& box, doub
 void ThermalCase::updateSources()
 {
     const size_t n = (size_t)dims.nCells();
+    ProfScope ps_(ctx, PC_QDOT);
     B200_CUDA(cudaMemsetAsync(qDot, 0, n * sizeof(double), ctx->stream));
     for (auto& hs : sources) {
         if (!hs.beam.activePath(time_)) continue;
@@ -344,6 +351,7 @@ void ThermalCase::updateCoeffsT()
 // T.correctBoundaryConditions(): evaluate() calls updateCoeffs() when the patch is not updated, then resets the flag
 void ThermalCase::evaluateT()
 {
+    ProfScope ps_(ctx, PC_BOUNDARY);
     updateCoeffsT();
     for (int sd = 0; sd < 6; sd++) {
         SideInfo& si = sides[sd];
@@ -368,13 +376,13 @@ void ThermalCase::assembleBase(bool explicitSolve, double rDeltaT)
                                                                si.valueFraction, si.Tb, si.intCoeff, si.bouCoeff, 0, 1, si.n);
             B200_LAUNCH_CHECK();
         }
-        k_faces<false><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK();
-        k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho); B200_LAUNCH_CHECK();
+        { ProfScope ps_(ctx, PC_FACES); k_faces<false><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
+        { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho); B200_LAUNCH_CHECK(); }
     } else {
         haloExchange(T);
-        k_faces<true><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK();
-        k_assemble_explicit<<<grid, BLK, 0, s>>>(dims, geo, sidesDev, Cp, Told, T, qDot, upper, rKappa, diag0, source0, rDeltaT, mat.rho);
-        B200_LAUNCH_CHECK();
+        { ProfScope ps_(ctx, PC_FACES); k_faces<true><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
+        { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_explicit<<<grid, BLK, 0, s>>>(dims, geo, sidesDev, Cp, Told, T, qDot, upper, rKappa, diag0, source0, rDeltaT, mat.rho);
+        B200_LAUNCH_CHECK(); }
     }
 }
 
@@ -388,15 +396,16 @@ void ThermalCase::step(b200_step_report* rep)
     setDeltaT(alphaCoMax, diMax);                                      // :72
     updateSources();                                                   // :74
     // runTime++ (:76)
+    { ProfScope ps_(ctx, PC_COPY);
     B200_CUDA(cudaMemcpyAsync(Told, T, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
-    B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
     time_ += deltaT_; timeIndex++;
     if (ctl.writeInterval > 0) {
         const int wi = int(((time_ - ctl.startTime) + 0.5 * deltaT_) / ctl.writeInterval);
         if (wi > writeTimeIndex) writeTimeIndex = wi;
     }
     // solutionControls.H
-    k_power<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, qDot, geo.V, red); B200_LAUNCH_CHECK();
+    { ProfScope ps_(ctx, PC_QDOT); k_power<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, qDot, geo.V, red); B200_LAUNCH_CHECK(); }
     ctx->allreduceSum(red.result + R_POWER, 1);
     d2h(h_red + R_POWER, red.result + R_POWER, 1, s);
     ctx->sync();
@@ -426,13 +435,13 @@ void ThermalCase::step(b200_step_report* rep)
     double residual = 0;
     for (int tCorr = 0; tCorr < nThermoCorr; tCorr++) {
         if (explicitSolve) {
-            k_corrector<true><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK();
+            { ProfScope ps_(ctx, PC_CORRECTOR); k_corrector<true><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK(); }
             perf = SolvePerf(); perf.converged = 1;
         } else {
-            k_corrector<false><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK();
+            { ProfScope ps_(ctx, PC_CORRECTOR); k_corrector<false><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK(); }
             perf = ldu->solve(A, source, T, sc);
             iterSum += perf.nIterations;
-            k_alpha_update<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, T, dFdT, T0, alpha1, red); B200_LAUNCH_CHECK();
+            { ProfScope ps_(ctx, PC_ALPHA); k_alpha_update<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, T, dFdT, T0, alpha1, red); B200_LAUNCH_CHECK(); }
         }
         evaluateT();                                                   // T.correctBoundaryConditions()
         ctx->allreduceMax(red.result + R_RESID, 1);

@@ -24,7 +24,8 @@ dp, ip = abi.c_double_p, abi.c_int32_p
 #: every symbol include/additivefoam_b200.h declares
 SYMBOLS = [
     "b200_last_error", "b200_abi_version", "b200_nccl_unique_id", "b200_ctx_create", "b200_ctx_destroy",
-    "b200_ctx_synchronize", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
+    "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
+    "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
     "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_kernel_launches",
@@ -52,6 +53,12 @@ def load():
     L.b200_ctx_create.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.b200_ctx_destroy.argtypes = [vp]
     L.b200_ctx_synchronize.argtypes = [vp]
+    L.b200_ctx_mark.argtypes = [vp, C.c_int]
+    L.b200_ctx_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
+    L.b200_profile_enable.argtypes = [vp, C.c_int]
+    L.b200_profile_name.restype = C.c_char_p
+    L.b200_profile_name.argtypes = [C.c_int]
+    L.b200_profile_read.argtypes = [vp, dp, C.POINTER(C.c_int64), C.c_int]
     L.b200_ldu_create.argtypes = [vp, C.c_int32, C.c_int32, ip, ip, C.c_int32, ip, ip, C.POINTER(ip), C.POINTER(vp)]
     L.b200_ldu_destroy.argtypes = [vp]
     L.b200_ldu_set_block.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
@@ -114,6 +121,26 @@ class Context:
 
     def synchronize(self):
         _check(self.L.b200_ctx_synchronize(self.h))
+
+    def mark(self, i):
+        """Record CUDA event ``i`` (0..3) on the library's stream."""
+        _check(self.L.b200_ctx_mark(self.h, i))
+
+    def elapsed_ms(self, i, j):
+        ms = C.c_double()
+        _check(self.L.b200_ctx_elapsed_ms(self.h, i, j, C.cast(C.byref(ms), dp)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        _check(self.L.b200_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{group: (total_ms, launches)} since the last read; synchronises."""
+        n = self.L.b200_profile_groups()
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        _check(self.L.b200_profile_read(self.h, ms, cnt, n))
+        return {self.L.b200_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
 
     def kernel_launches(self):
         n = C.c_int64()
@@ -225,6 +252,14 @@ class Case:
         a = _f64(a)
         assert a.size == self.n_local
         _check(self.L.b200_case_set_field(self.h, f, _P(a)))
+
+    def field_into(self, f, out):
+        """get_field into an existing (e.g. pinned) array."""
+        _check(self.L.b200_case_get_field(self.h, f, _P(out)))
+
+    def set_field_keep_old(self, f, a):
+        """set_field without touching the old-time copy (host application owns the field between steps)."""
+        _check(self.L.b200_case_set_field(self.h, f | 0x100, _P(a)))
 
     def close(self):
         if self.h:

@@ -53,7 +53,10 @@ enum { B200_KELLY_CONE = 0, B200_KELLY_CYLINDER = 1 };
 enum {
     B200_FIELD_T = 0, B200_FIELD_ALPHA_SOLID = 1, B200_FIELD_ALPHA_POWDER = 2,
     B200_FIELD_KAPPA = 3, B200_FIELD_CP = 4, B200_FIELD_QDOT = 5,
-    B200_FIELD_DFDT = 6, B200_FIELD_T0 = 7
+    B200_FIELD_DFDT = 6, B200_FIELD_T0 = 7,
+    /* OR-ed into the field id of b200_case_set_field: upload only, leave the old-time copy and the patch state alone
+     * (a host application that owns the field between steps re-uploads the same values) */
+    B200_FIELD_KEEP_OLD = 0x100
 };
 
 /* ------------------------------------------------------- case description */
@@ -171,6 +174,16 @@ int  b200_nccl_unique_id(void* out128);
 int  b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, int nranks, b200_ctx** out);
 int  b200_ctx_destroy(b200_ctx* ctx);
 int  b200_ctx_synchronize(b200_ctx* ctx);
+/* CUDA events on the library's own stream (bench.py times the step with these): record mark i (0..3);
+ * elapsed ms between two recorded marks (synchronises). */
+int  b200_ctx_mark(b200_ctx* ctx, int i);
+int  b200_ctx_elapsed_ms(b200_ctx* ctx, int i, int j, double* ms);
+/* Built-in per-kernel-group timing (CUDA event pair around every launch group).  read() synchronises, fills
+ * ms[n]/counts[n] for the first n groups and resets the accumulators; names by index. */
+int  b200_profile_enable(b200_ctx* ctx, int on);
+int  b200_profile_groups(void);
+const char* b200_profile_name(int group);
+int  b200_profile_read(b200_ctx* ctx, double* ms, int64_t* counts, int n);
 
 /* ---- B1: lduMatrix::solver.  Addressing is cached in the handle; coefficients are per call.
  * lower/upper: [UPSTREAM] lduAddressing::lowerAddr()/upperAddr() (upper-triangular order).
