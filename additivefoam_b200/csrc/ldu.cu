@@ -1,4 +1,6 @@
 #include "ldu_kernels.cuh"
+#include "wave_kernels.cuh"
+#include <cstdlib>
 #include "ctx.cuh"
 #include <algorithm>
 #include <cstring>
@@ -95,6 +97,8 @@ Ldu::Ldu(Ctx* c, BlockDims d) : ctx(c), dims(d)
     nCells = (int)d.nCells(); nFaces = (int)d.nFaces();
     isBlock = true; hasGeneral = false;
     nLevels = d.nx + d.ny + d.nz - 2;
+    const char* e = std::getenv("B200_SWEEP");
+    useWave = !(e && std::string(e) == "coop");
 }
 
 Ldu::~Ldu()
@@ -108,6 +112,9 @@ Ldu::~Ldu()
     if (h_state) cudaFreeHost(h_state);
     dev_free(red.partials); dev_free(red.ticket); dev_free(red.result);
     for (auto& p : stage) dev_free(p);
+    for (auto& p : stageBou) dev_free(p);
+    for (auto& p : wave) dev_free(p);
+    dev_free(waveFlags); dev_free(wavePartial);
 }
 
 void Ldu::setBlock(int nx, int ny, int nz)
@@ -125,6 +132,8 @@ void Ldu::setBlock(int nx, int ny, int nz)
     dev_free(lo); dev_free(up);
     B200_CHECK(hl == h_lower && hu == h_upper, "addressing is not a single blockMesh hex block of these dimensions");
     dims = d; isBlock = true;
+    const char* e = std::getenv("B200_SWEEP");
+    useWave = !(e && std::string(e) == "coop");
     for (auto& w : work) dev_free(w);       // ghost padding changes
     dev_free(rD);
 }
@@ -249,6 +258,51 @@ void Ldu::amul(const MatrixView& A, const double* psi, double* Apsi)
     amulFused(A, psi, Apsi, AM_NONE, nullptr);
 }
 
+// ------------------------------------------------------------------ tile-wavefront sweeps (block addressing)
+static WaveGeom wave_geom(const BlockDims& d)
+{
+    WaveGeom g;
+    g.nx = d.nx; g.ny = d.ny; g.nz = d.nz;
+    g.nJ = (d.ny + WTJ - 1) / WTJ; g.nK = (d.nz + WTK - 1) / WTK; g.nTiles = g.nJ * g.nK;
+    g.nSteps = d.nx + WTJ + WTK - 2;
+    g.nStepsPad = (g.nSteps + 2 * WS - 1) / (2 * WS) * (2 * WS);      // an even number of WS-step groups
+    g.nxny = (int64_t)d.nx * d.ny;
+    return g;
+}
+
+void Ldu::ensureWave(bool dilu)
+{
+    const WaveGeom g = wave_geom(dims);
+    waveLen = (int64_t)g.nTiles * g.nStepsPad * 32;
+    const int nArr = dilu ? 13 : 10;
+    for (int q = 0; q < nArr; q++)
+        if (!wave[q]) { wave[q] = dev_alloc<double>((size_t)waveLen); B200_CUDA(cudaMemsetAsync(wave[q], 0, (size_t)waveLen * sizeof(double), ctx->stream)); }
+    if (!waveFlags) { waveFlags = dev_alloc<int>(4); wavePartial = dev_alloc<double>(g.nTiles); }
+}
+
+// op: 0 factor (after the gather), 1 forward, 2 backward
+void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
+{
+    WaveArgs a;
+    a.g = wave_geom(dims);
+    a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
+    a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12];
+    a.rA = rA; a.wA = wA;
+    a.ticket = waveFlags; a.tilePartial = wavePartial; a.st = d_state;
+    cudaStream_t s = ctx->stream;
+    B200_CUDA(cudaMemsetAsync(waveFlags, 0, sizeof(int), s));
+    // the factor sweep exchanges raw rD through RF: arm it with the sentinel (all-ones NaN); the factor sweep itself arms
+    // WF and WB for the substitution sweeps, which then re-arm each other's array as they go
+    if (op == 0) B200_CUDA(cudaMemsetAsync(wave[8], 0xFF, (size_t)waveLen * sizeof(double), s));
+    const int grid = a.g.nTiles;
+    if (op == 0) { if (dilu) k_wave<0, true, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false><<<grid, 32, 0, s>>>(a); }
+    else if (op == 1) k_wave<1, false, false><<<grid, 32, 0, s>>>(a);
+    else if (dot) k_wave<2, false, true><<<grid, 32, 0, s>>>(a);
+    else k_wave<2, false, false><<<grid, 32, 0, s>>>(a);
+    B200_LAUNCH_CHECK();
+    if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }
+}
+
 // ------------------------------------------------------------------ preconditioners
 void Ldu::factor(int kind, const MatrixView& A)
 {
@@ -262,7 +316,20 @@ void Ldu::factor(int kind, const MatrixView& A)
         const bool dilu = kind == 3;
         double* rd = rD + ghost;
         const double* nul = nullptr; double* nulw = nullptr;
-        if (isBlock) {
+        if (isBlock && useWave) {
+            ensureWave(dilu);
+            WaveArgs a;
+            a.g = wave_geom(dims);
+            a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
+            a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.st = st;
+            const int64_t rows = (int64_t)a.g.nTiles * a.g.nStepsPad;
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->smCount * 16));
+            if (dilu) k_wave_gather<true><<<grid, 256, 0, s>>>(dims, a, A.diag, A.upper, A.lower);
+            else k_wave_gather<false><<<grid, 256, 0, s>>>(dims, a, A.diag, A.upper, A.lower);
+            B200_LAUNCH_CHECK();
+            waveSweep(0, dilu, false, nullptr, nullptr);
+            return;          // rD lives in wave order (A0); P*, Q* are already scaled by it
+        } else if (isBlock) {
             if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
             else coop_launch(ctx, k_sweep_block<0, false, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
         } else {
@@ -284,7 +351,11 @@ void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* 
     if (kind == 1) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<true><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
     const bool dilu = kind == 3;
     const double* nul = nullptr;
-    if (isBlock) {
+    if (isBlock && useWave) {
+        { ProfScope ps_(ctx, PC_SWEEP_FWD); waveSweep(1, dilu, false, rA, wA); }
+        { ProfScope ps_(ctx, PC_SWEEP_BWD); waveSweep(2, dilu, doDot != 0, rA, wA); }
+        B200_CHECK(!doDot || dotVec == rA, "fused preconditioner dot product is defined against rA");
+    } else if (isBlock) {
         const int64_t work_ = (int64_t)dims.ny * dims.nz;
         if (dilu) { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, true, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
         else { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }

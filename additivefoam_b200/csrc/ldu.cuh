@@ -112,8 +112,14 @@ public:
     SolveState* h_state = nullptr;   // pinned
     RedWork red{};
     int redBlocks = 1;
-    // factor cache key
-    const double* factoredDiag = nullptr;
+    // tile-wavefront sweeps (block addressing): coefficient arrays renumbered into wave order
+    bool useWave = true;
+    double* wave[13] = {nullptr};    // A0 PX PY PZ QX QY QZ WF RF WB NX NY NZ
+    int* waveFlags = nullptr;        // tile ticket
+    double* wavePartial = nullptr;
+    int64_t waveLen = 0;
+    void ensureWave(bool dilu);
+    void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA);
 
     void ensureWork();
     double* vec(int i) { return work[i] + ghost; }
