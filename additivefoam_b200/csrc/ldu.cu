@@ -450,7 +450,10 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     if (!pcg) { { ProfScope ps_(ctx, PC_VECTOR); k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); } }
 
     const int hardMax = std::max(sc.maxIter + 1, sc.minIter);
-    int enqueued = 0, chunk = 2;
+    // Large systems: look at the convergence flag after every iteration (one tiny D2H + sync against milliseconds of
+    // kernels), so no launch is wasted; small systems: enqueue several iterations per look, later ones become no-ops.
+    const bool perIteration = nCells >= (1 << 20);
+    int enqueued = 0, chunk = perIteration ? 1 : 2;
     for (;;) {
         for (int it = 0; it < chunk && enqueued < hardMax; it++, enqueued++) {
             if (pcg) {
@@ -490,7 +493,7 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
         d2h(h_state, d_state, 1, s);
         ctx->sync();
         if (h_state->done || enqueued >= hardMax) break;
-        chunk = std::min(chunk * 2, 32);
+        if (!perIteration) chunk = std::min(chunk * 2, 32);
     }
     perf.initialResidual = h_state->initRes; perf.finalResidual = h_state->finalRes;
     perf.nIterations = h_state->nIter; perf.converged = h_state->converged; perf.singular = h_state->singular;
