@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(BLK) k_dinum(BlockDims d, Geom g, SidesDev sd,
         if (i < nx - 1) { const double kN = kappa[c + 1]; S += g.sfx * (0.5 * (kc - kN) + kN) * g.dcx; }
         if (j < d.ny - 1) { const double kN = kappa[c + nx]; S += g.sfy * (0.5 * (kc - kN) + kN) * g.dcy; }
         if (k < d.nz - 1) { const double kN = kappa[c + nxny]; S += g.sfz * (0.5 * (kc - kN) + kN) * g.dcz; }
-        for (int q = 0; q < sd.nOrder; q++) {
+        const bool bnd = i == 0 || i == nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
+        for (int q = 0; bnd && q < sd.nOrder; q++) {
             const int s = sd.order[q];
             if (!on_side(d, s, i, j, k)) continue;
             if (sd.type[s] == SIDE_PROCESSOR) {
@@ -244,7 +245,8 @@ __global__ void __launch_bounds__(BLK) k_assemble_explicit(BlockDims d, Geom g, 
         if (fx >= 0) lap += kf[fx] * (g.dcx * (T[c + 1] - Tc)) * g.sfx;
         if (fy >= 0) lap += kf[fy] * (g.dcy * (T[c + nx] - Tc)) * g.sfy;
         if (fz >= 0) lap += kf[fz] * (g.dcz * (T[c + nxny] - Tc)) * g.sfz;
-        for (int q = 0; q < sd.nOrder; q++) {
+        const bool bnd = i == 0 || i == nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
+        for (int q = 0; bnd && q < sd.nOrder; q++) {
             const int s = sd.order[q];
             if (!on_side(d, s, i, j, k)) continue;
             const int type = sd.type[s];
@@ -317,11 +319,12 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         double dg = (a.diag0[c] + diag1) - diag2;
         double sr = (a.source0[c] + source1) - sourceR;
         if (!EXPLICIT) {      // the explicit matrix has zero boundary coefficients
-            for (int q = 0; q < sd.nOrder; q++) {
+            const bool bnd = i == 0 || i == d.nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
+            for (int q = 0; bnd && q < sd.nOrder; q++) {
                 const int s = sd.order[q];
                 if (on_side(d, s, i, j, k)) dg += sd.intCoeff[s][side_index(d, s, i, j, k)];
             }
-            for (int q = 0; q < sd.nOrder; q++) {
+            for (int q = 0; bnd && q < sd.nOrder; q++) {
                 const int s = sd.order[q];
                 if (sd.type[s] != SIDE_PROCESSOR && on_side(d, s, i, j, k)) sr += sd.bouCoeff[s][side_index(d, s, i, j, k)];
             }

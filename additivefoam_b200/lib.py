@@ -39,6 +39,26 @@ class B200Error(RuntimeError):
     pass
 
 
+def _preload_nccl():
+    """libadditivefoam_b200.so links libnccl.so.2 by soname.  PyTorch bundles a newer NCCL under the same soname; if ours
+    pulled the system copy in first, a later ``import torch`` would bind to it and fail.  Load the bundled one first."""
+    import glob
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+        roots = list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []
+    except Exception:
+        roots = []
+    for r in roots:
+        for so in glob.glob(os.path.join(r, "lib", "libnccl.so*")):
+            try:
+                C.CDLL(so, mode=C.RTLD_GLOBAL)
+                return so
+            except OSError:
+                continue
+    return None
+
+
 def load():
     """Load the CUDA library; raises if it has not been built (``python -c 'import __graft_entry__ as g; g.build()'``)."""
     global _lib
@@ -46,7 +66,8 @@ def load():
         return _lib
     if not os.path.exists(SO_PATH):
         raise B200Error(f"{SO_PATH} is missing: build it with additivefoam_b200/csrc/Makefile; there is no CPU fallback")
-    L = C.CDLL(SO_PATH, mode=C.RTLD_GLOBAL)
+    _preload_nccl()
+    L = C.CDLL(SO_PATH)
     L.b200_last_error.restype = C.c_char_p
     vp = C.c_void_p
     L.b200_nccl_unique_id.argtypes = [vp]

@@ -1,0 +1,324 @@
+"""The CPU oracle against the known answers derived from the reference formulas and against
+independent dense / analytic solutions.  The reference ships no golden vectors, so these anchors
+are what pins the oracle ("parity unpinned" at the OpenFOAM-10 boundary: see oracle/af_ldu.hpp)."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import helpers
+import oracle_lib as ol
+from additivefoam_b200 import abi, cases
+
+P = ol.P
+PATH = [[1, 0.0, 0.0, 0.0, 0.0, 0.0], [0, 0.002, 0.0, 0.0, 179.2, 0.8]]
+
+
+def dims3(v):
+    a = np.array(v, dtype=np.float64)
+    return P(a), a
+
+
+# ---------------------------------------------------------------- heat source formulas
+def test_super_gaussian_V0(oracle):
+    """superGaussian.C:73-85, k = 2, dims (85, 85, 30) um."""
+    b = cases.make_beam(cases.super_gaussian_beam(PATH))
+    p, keep = dims3((85e-6, 85e-6, 30e-6))
+    assert oracle.afo_shape_V0(C.byref(b), p) == pytest.approx(2.1335799723345844e-13, rel=1e-14)
+
+
+def test_modified_super_gaussian_V0(oracle):
+    """modifiedSuperGaussian.C:87-103, k = 7.95, m = 2.72, dims (40, 40, 30) um."""
+    b = cases.make_beam(cases.modified_super_gaussian_beam(PATH))
+    p, keep = dims3((40e-6, 40e-6, 30e-6))
+    assert oracle.afo_shape_V0(C.byref(b), p) == pytest.approx(8.921206515601453e-14, rel=1e-13)
+
+
+def test_projected_gaussian_k_follows_depth(oracle):
+    """projectedGaussian.C:96-118: n = clamp(A*log2(max(dz/min(dx0,dy0),1)) + B, 0, 9), k = 2^n, V0 analytic."""
+    spec = cases.projected_gaussian_beam(PATH, dims=(50e-6, 50e-6, 30e-6), A=2.0, B=1.0)
+    b = cases.make_beam(spec)
+    for dz in (30e-6, 100e-6, 400e-6):
+        p, keep = dims3((50e-6, 50e-6, dz))
+        n = min(max(2.0 * math.log2(max(dz / 50e-6, 1.0)) + 1.0, 0.0), 9.0)
+        k = 2.0 ** n
+        want = 0.5 * math.pi * 50e-6 * 50e-6 * dz * math.gamma(1.0 / k) / (k * 3.0 ** (1.0 / k))
+        assert oracle.afo_shape_V0(C.byref(b), p) == pytest.approx(want, rel=1e-13)
+
+
+def test_shape_weights_pointwise(oracle):
+    b = cases.make_beam(cases.super_gaussian_beam(PATH, k=2.0))
+    pd, keepd = dims3((85e-6, 85e-6, 30e-6))
+    pv, keepv = dims3((85e-6 / math.sqrt(2.0), 0.0, 0.0))          # one scaled radius: exp(-1)
+    assert oracle.afo_shape_weight(C.byref(b), pd, pv) == pytest.approx(math.exp(-1.0), rel=1e-13)
+    m = cases.make_beam(cases.modified_super_gaussian_beam(PATH))
+    pd, keepd = dims3((40e-6, 40e-6, 30e-6))
+    pv, keepv = dims3((0.0, 0.0, 30e-6))                            # at the tip: outside (d.z < s.z fails)
+    assert oracle.afo_shape_weight(C.byref(m), pd, pv) == 0.0
+    pv, keepv = dims3((0.0, 0.0, 0.0))
+    assert oracle.afo_shape_weight(C.byref(m), pd, pv) == 1.0
+
+
+def test_kelly_absorption(oracle):
+    """KellyAbsorption.C:67-99, cone, eta0 = 0.28, etaMin = 0.35; discontinuous at aspect ratio 1."""
+    b = cases.make_beam(cases.modified_super_gaussian_beam(PATH))
+    assert oracle.afo_absorption_eta(C.byref(b), 0.75) == 0.35
+    assert oracle.afo_absorption_eta(C.byref(b), 1.0) == 0.35
+    assert oracle.afo_absorption_eta(C.byref(b), 2.0) == pytest.approx(0.6453157893721592, rel=1e-14)
+    assert oracle.afo_absorption_eta(C.byref(b), 1.0 + 1e-12) == pytest.approx(0.5054, abs=5e-5)
+    spec = cases.modified_super_gaussian_beam(PATH)
+    spec["kellyGeometry"] = abi.KELLY_CYLINDER
+    c = cases.make_beam(spec)
+    a, e0 = 3.0, 0.28
+    th = math.atan(1 / a)
+    F, G = 0.5 * (1 - math.cos(2 * th)), 0.5 / (1 + a)
+    assert oracle.afo_absorption_eta(C.byref(c), a) == pytest.approx(e0 * (1 + (1 - e0) * (G - F)) / (1 - (1 - e0) * (1 - G)), rel=1e-14)
+
+
+def test_constant_absorption_and_peak_qdot(oracle):
+    b = cases.make_beam(cases.super_gaussian_beam(PATH))
+    assert oracle.afo_absorption_eta(C.byref(b), 0.35) == 0.33
+    assert 0.33 * 179.2 == pytest.approx(59.136)
+    assert 59.136 / 2.1335799723345844e-13 == pytest.approx(2.7717e14, rel=1e-4)
+
+
+# ---------------------------------------------------------------- beam kinematics
+def move(oracle, spec, times, start=0.0, end=1.0):
+    b = cases.make_beam(spec)
+    t = np.array(times, dtype=np.float64)
+    pos, pw, idx = np.empty(3 * len(t)), np.empty(len(t)), np.empty(len(t), dtype=np.int32)
+    et = C.c_double()
+    oracle.afo_beam_move(C.byref(b), start, end, len(t), P(t), P(pos), P(pw), P(idx), C.cast(C.byref(et), abi.c_double_p))
+    return pos.reshape(-1, 3), pw, idx, et.value
+
+
+def test_moving_beam_amb2018(oracle):
+    """movingBeam.C:157-225: the shipped path is a zero-dwell point then a 2 mm line at 0.8 m/s (2.5 ms)."""
+    pos, pw, idx, endTime = move(oracle, cases.super_gaussian_beam(PATH), [0.0, 5e-11, 1e-9, 1.25e-3, 2.5e-3, 3e-3], end=0.004)
+    assert endTime == pytest.approx(2.5e-3)
+    assert list(idx) == [2, 2, 2, 2, 2, 2]                      # the zero-dwell point source is skipped (findIndex)
+    assert pw[0] == 0.0 and pw[1] == 0.0                          # power switches only after eps = 1e-10
+    assert pw[2] == 179.2 and pw[3] == 179.2
+    assert pos[3, 0] == pytest.approx(1e-3) and pos[4, 0] == pytest.approx(2e-3)
+    assert pos[5, 0] == pytest.approx(2.4e-3)                    # linear extrapolation past the last segment
+
+
+def test_moving_beam_dwell_and_raster(oracle):
+    path = [[1, 0, 0, 0, 0, 0], [0, 1e-3, 0, 0, 100.0, 1.0], [1, 1e-3, 1e-4, 0, 0.0, 5e-4], [0, 0, 1e-4, 0, 100.0, 1.0]]
+    pos, pw, idx, endTime = move(oracle, cases.super_gaussian_beam(path), [5e-4, 1.2e-3, 1.5e-3, 2.0e-3, 2.5e-3], end=1.0)
+    assert endTime == pytest.approx(2.5e-3)
+    assert pos[0, 0] == pytest.approx(5e-4) and pw[0] == 100.0
+    assert list(idx[1:3]) == [3, 3] and pw[1] == 0.0 and pos[1, 1] == pytest.approx(1e-4)      # dwelling at the turn
+    assert idx[3] == 4 and pos[3, 0] == pytest.approx(5e-4) and pw[3] == 100.0
+
+
+def test_adjust_deltaT_hits_path_end(oracle):
+    """movingBeam.C:228-256: the step is shrunk to land on the segment boundary, dilated at most 1 %."""
+    b = cases.make_beam(cases.super_gaussian_beam(PATH))
+    dt = oracle.afo_beam_adjust_deltaT(C.byref(b), 0.0, 0.004, 2.49e-3, 2.49e-3, 7e-6)
+    assert dt == pytest.approx(1e-5 / 2)                          # 10 us left, 7 us steps -> two steps of 5 us
+    dt = oracle.afo_beam_adjust_deltaT(C.byref(b), 0.0, 0.004, 2.49e-3, 2.49e-3, 9.95e-6)
+    assert dt == pytest.approx(9.95e-6)                           # within the 1 % dilation: one step, unchanged
+
+
+def test_scan_path_parse(oracle):
+    text = "Mode X Y Z Power Param\n1 0.000 0.000 0 0 0\n\n0 0.002 0.000 0 179.2 0.8\n"
+    out = np.empty(6 * 8)
+    n = oracle.afo_scan_path_parse(text.encode(), P(out), 8)
+    assert n == 2 and list(out[6:12]) == [0, 0.002, 0, 0, 179.2, 0.8]
+
+
+def test_interpolateXY_descending_table(oracle):
+    """interpolateXY.C:33-109 tolerates descending abscissae; Tliq/Tsol come from swapping the columns (createFields.H:59-71)."""
+    T, a = np.array([1410.0, 1620.0]), np.array([1.0, 0.0])
+    f = lambda x, X, Y: oracle.afo_interpolateXY(x, len(X), P(X), P(Y))      # noqa: E731
+    assert f(0.0, a, T) == 1620.0 and f(1.0, a, T) == 1410.0
+    assert f(1515.0, T, a) == pytest.approx(0.5)
+    assert f(300.0, T, a) == 1.0 and f(3000.0, T, a) == 0.0
+
+
+# ---------------------------------------------------------------- mesh / addressing
+@pytest.mark.parametrize("n,cells,faces", [((150, 25, 15), 56250, 162375), ((200, 100, 1), 20000, 39700)])
+def test_mesh_counts(oracle, n, cells, faces):
+    nc, nf, lo, up = ol.block_addressing(oracle, n)
+    assert (nc, nf) == (cells, faces)
+    assert np.all(lo < up) and np.all(np.diff(lo) >= 0)           # upper-triangular order
+    same = lo[1:] == lo[:-1]
+    assert np.all(up[1:][same] > up[:-1][same])
+
+
+def test_addressing_matches_numpy(oracle):
+    for n in [(4, 3, 2), (1, 5, 1), (7, 1, 3)]:
+        nc, nf, lo, up = ol.block_addressing(oracle, n)
+        lo2, up2 = helpers.block_addressing_np(n)
+        assert np.array_equal(lo, lo2) and np.array_equal(up, up2)
+
+
+def test_slab_decomposition_addressing(oracle):
+    """Rank r of R owns global k in [nz*r/R, nz*(r+1)/R); local order = global order restricted to the rank."""
+    n, R = (5, 4, 7), 3
+    total = 0
+    for r in range(R):
+        nc, nf, lo, up = ol.block_addressing(oracle, n, r, R)
+        nzl = 7 * (r + 1) // R - 7 * r // R
+        lo2, up2 = helpers.block_addressing_np((5, 4, nzl))
+        assert nc == 20 * nzl and np.array_equal(lo, lo2) and np.array_equal(up, up2)
+        total += nc
+    assert total == 140
+
+
+def test_levels_are_hyperplanes(oracle):
+    n = (6, 5, 4)
+    nc, nf, lo, up = ol.block_addressing(oracle, n)
+    lv = np.empty(nc, dtype=np.int32)
+    nl = C.c_int32()
+    oracle.afo_ldu_levels(nc, nf, P(lo), P(up), P(lv), C.byref(nl))
+    i, j, k = np.meshgrid(range(6), range(5), range(4), indexing="ij")
+    want = (i + j + k).transpose(2, 1, 0).ravel()
+    assert nl.value == 6 + 5 + 4 - 2 and np.array_equal(lv, want)
+
+
+# ---------------------------------------------------------------- LDU kernels against dense algebra
+def test_amul_and_preconditioners_against_dense(oracle):
+    n = 60
+    lo, up = helpers.random_ldu_addressing(n, 80, 7)
+    for asym in (False, True):
+        diag, upper, lower, x, b = helpers.spd_coefficients(n, lo, up, seed=8, asym=asym)
+        A = helpers.dense_from_ldu(n, lo, up, diag, upper, lower)
+        y = np.empty(n)
+        oracle.afo_ldu_amul(n, len(lo), P(lo), P(up), P(diag), P(upper), P(lower), P(x), P(y))
+        assert np.allclose(y, A @ x, rtol=1e-13, atol=1e-13)
+        # DIC / DILU = (D' + L) D'^-1 (D' + U) with D' from the incomplete factorisation restricted to the diagonal
+        kind = abi.PRECOND_DILU if asym else abi.PRECOND_DIC
+        w, rD = np.empty(n), np.empty(n)
+        oracle.afo_ldu_precondition(n, len(lo), P(lo), P(up), P(diag), P(upper), P(lower), kind, P(b), P(w), P(rD))
+        Lm, Um = np.tril(A, -1), np.triu(A, 1)
+        Dp = np.diag(1.0 / rD)
+        M = (Dp + Lm) @ np.diag(rD) @ (Dp + Um)
+        assert np.allclose(M @ w, b, rtol=1e-11, atol=1e-12)
+        # and D' satisfies its defining recurrence
+        d = diag.copy()
+        lw = upper if lower is None else lower
+        for f in range(len(lo)):
+            d[up[f]] -= upper[f] * lw[f] / d[lo[f]]
+        assert np.allclose(1.0 / d, rD, rtol=1e-13)
+
+
+@pytest.mark.parametrize("solver,precond,asym", [(abi.SOLVER_PCG, abi.PRECOND_DIC, False), (abi.SOLVER_PCG, abi.PRECOND_DIAGONAL, False),
+                                                 (abi.SOLVER_PBICGSTAB, abi.PRECOND_DILU, True), (abi.SOLVER_PBICGSTAB, abi.PRECOND_NONE, True)])
+def test_krylov_solvers_against_dense(oracle, solver, precond, asym):
+    n = 120
+    lo, up = helpers.random_ldu_addressing(n, 200, 9)
+    diag, upper, lower, x0, b = helpers.spd_coefficients(n, lo, up, seed=10, asym=asym)
+    A = helpers.dense_from_ldu(n, lo, up, diag, upper, lower)
+    x = x0.copy()
+    perf = abi.SolverPerf()
+    log, nlog = np.empty(512), C.c_int32()
+    oracle.afo_ldu_solve(n, len(lo), P(lo), P(up), P(diag), P(upper), P(lower), P(b), P(x), solver, precond, 1e-12, 0.0, 0, 400,
+                         C.byref(perf), P(log), 512, C.byref(nlog))
+    assert perf.converged and np.allclose(x, np.linalg.solve(A, b), rtol=1e-8, atol=1e-10)
+    # residual normalisation: [UPSTREAM] lduMatrix::solver::normFactor
+    xbar = x0.mean()
+    sumA = A.sum(axis=1)
+    nf = np.abs(A @ x0 - xbar * sumA).sum() + np.abs(b - xbar * sumA).sum() + 1e-20
+    assert perf.initialResidual == pytest.approx(np.abs(b - A @ x0).sum() / nf, rel=1e-12)
+    assert log[0] == perf.initialResidual and log[nlog.value - 1] == perf.finalResidual
+
+
+def test_max_iter_is_post_increment(oracle):
+    """do {...} while (nIterations()++ < maxIter_ && !converged): an unconverged solve reports maxIter + 1 iterations
+    (the familiar 'No Iterations 1001' of OpenFOAM logs); minIter forces at least that many."""
+    n = 200
+    lo, up = helpers.random_ldu_addressing(n, 300, 11)
+    diag, upper, lower, x0, b = helpers.spd_coefficients(n, lo, up, seed=12)
+    diag = -np.bincount(lo, upper, n) - np.bincount(up, upper, n) + 1e-6
+    for maxIter, want in [(3, 4), (20, 21)]:
+        x = x0.copy()
+        perf = abi.SolverPerf()
+        oracle.afo_ldu_solve(n, len(lo), P(lo), P(up), P(diag), P(upper), None, P(b), P(x), abi.SOLVER_PCG, abi.PRECOND_DIC, 1e-15, 0.0,
+                             1, maxIter, C.byref(perf), None, 0, None)
+        assert perf.nIterations == want and not perf.converged
+    x = b / diag
+    perf = abi.SolverPerf()
+    oracle.afo_ldu_solve(n, 0, P(lo[:0].copy()), P(up[:0].copy()), P(diag), P(upper[:0].copy()), None, P(b), P(x), abi.SOLVER_PCG,
+                         abi.PRECOND_DIAGONAL, 1e-6, 0.0, 3, 20, C.byref(perf), None, 0, None)
+    assert perf.nIterations == 3 or perf.singular              # minIter honoured unless the residual is exactly zero
+
+
+# ---------------------------------------------------------------- the case as a whole
+def test_material_anchors(oracle):
+    c = ol.OracleCase(cases.amb2018_02_b(n=(6, 5, 4)), lib=oracle)
+    assert oracle.afo_case_Tliq(c.h) == 1620.0 and oracle.afo_case_Tsol(c.h) == 1410.0
+    assert np.all(c.field(abi.FIELD_ALPHA_SOLID) == 1.0)
+    kap, cp = c.field(abi.FIELD_KAPPA), c.field(abi.FIELD_CP)
+    assert kap[0] == pytest.approx(8.275 + 0.01472 * 300.0, rel=1e-15) and cp[0] == 579.28
+    hot = np.full(c.n, 1700.0)
+    c.set_field(abi.FIELD_T, hot)
+    c.set_field(abi.FIELD_ALPHA_SOLID, np.zeros(c.n))
+    c.step()
+    # liquid conductivity is evaluated at clamp(T, Tliq, 2 Tliq); kappa_solid(1410) = 29.0302, kappa_liq(1620) = 28.77266
+    assert 8.275 + 0.01472 * 1410.0 == pytest.approx(29.0302)
+    assert 4.889 + 0.014743 * 1620.0 == pytest.approx(28.77266)
+    c.close()
+
+
+def test_power_is_conserved_every_step(oracle):
+    """Sum(V*qDot) = eta*P while the Riemann sum stays within 5 % of V0 (heatSourceModel.C:359-367)."""
+    c = ol.OracleCase(cases.amb2018_02_b(n=(75, 13, 8)), lib=oracle)
+    for _ in range(25):
+        r = c.step()
+        assert r.totalPower == pytest.approx(0.33 * 179.2, rel=1e-12)
+    c.close()
+
+
+def test_explicit_step_limit(oracle):
+    """alpha_th = kappa/(rho Cp) ~ 6.6e-6 m^2/s: Di = 1 at dt ~ 1.0e-5 s on 20 um cells; steps below it are explicit."""
+    c = ol.OracleCase(cases.amb2018_02_b(), lib=oracle)
+    reps = [c.step() for _ in range(45)]
+    assert all(r.explicitStep == 1 for r in reps)
+    assert max(r.DiNum for r in reps) <= 1.0 + 0.21            # growth capped at 1.2x per step
+    assert 5e-6 < reps[-1].deltaT < 1.05e-5
+    c.close()
+
+
+def test_conduction_only_keeps_energy(oracle):
+    """Lf = 0, constant properties, adiabatic walls: rho*Cp*V*sum(T - T0) == deposited energy (implicit PCG/DIC)."""
+    case = cases.rosenthal(n=(40, 16, 8), tolerance=1e-14, maxIter=200)
+    case["controls"]["deltaT"] = 2e-6
+    c = ol.OracleCase(case, lib=oracle)
+    V = (20e-6) ** 3
+    E = 0.0
+    for _ in range(20):
+        r = c.step()
+        E += r.totalPower * r.deltaT
+        assert r.explicitStep == 0
+    T = c.field(abi.FIELD_T)
+    stored = 7569.92 * 600.0 * V * np.sum(T - 300.0)
+    assert stored == pytest.approx(E, rel=1e-9)
+    c.close()
+
+
+def test_serial_vs_slab_decomposed(oracle):
+    """The z-slab decomposition (block-local DIC, processor interfaces) reproduces the serial fields."""
+    kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC)
+    a = ol.OracleCase(cases.amb2018_02_b(n=(40, 10, 9), **kw), ranks=1, lib=oracle)
+    b = ol.OracleCase(cases.amb2018_02_b(n=(40, 10, 9), **kw), ranks=3, lib=oracle)
+    for _ in range(40):
+        ra, rb = a.step(), b.step()
+        assert ra.deltaT == pytest.approx(rb.deltaT, rel=1e-10)
+    assert helpers.rel_linf(b.field(abi.FIELD_T), a.field(abi.FIELD_T)) < 1e-9
+    assert np.max(np.abs(b.field(abi.FIELD_ALPHA_SOLID) - a.field(abi.FIELD_ALPHA_SOLID))) < 1e-9
+    a.close(); b.close()
+
+
+def test_melt_pool_forms_and_solidifies(oracle):
+    """After the beam has passed, cells that melted are solid again and alpha.solid is back in [0, 1] everywhere."""
+    c = ol.OracleCase(cases.amb2018_02_b(n=(75, 13, 8)), lib=oracle)
+    minA = 1.0
+    for _ in range(150):
+        c.step()
+        minA = min(minA, c.field(abi.FIELD_ALPHA_SOLID).min())
+    a = c.field(abi.FIELD_ALPHA_SOLID)
+    assert minA < 0.5 and a.min() >= 0.0 and a.max() <= 1.0
+    c.close()

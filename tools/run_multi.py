@@ -1,0 +1,48 @@
+"""Decomposed GPU run (one z-slab per rank, torchrun) checked against the CPU oracle's in-process emulation of the same
+ranks.  Usage: torchrun --nproc-per-node N tools/run_multi.py [implicit|explicit] [steps]"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from additivefoam_b200 import abi, cases, lib, partition  # noqa: E402
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "implicit"
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+uid = partition.broadcast_unique_id(lib.nccl_unique_id, rank, dist, device="cuda")
+ctx = lib.Context(local, uid, rank, world)
+n = (48, 14, 11)
+kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC) if mode == "implicit" else dict()
+if mode == "bicg":
+    kw = dict(explicitSolve=0, maxDi=10.0)
+case = cases.amb2018_02_b(n=n, **kw)
+g = lib.Case(ctx, case)
+assert g.n_local == partition.local_cells(n, rank, world)
+reps = [g.step() for _ in range(steps)]
+T = partition.gather_field(g.field(abi.FIELD_T), n, rank, world, dist, device="cuda")
+A = partition.gather_field(g.field(abi.FIELD_ALPHA_SOLID), n, rank, world, dist, device="cuda")
+ok = True
+if rank == 0:
+    import oracle_lib as ol
+    o = ol.OracleCase(case, ranks=world)
+    oreps = [o.step() for _ in range(steps)]
+    To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
+    eT = float(np.max(np.abs(T - To)) / np.max(np.abs(To)))
+    eA = float(np.max(np.abs(A - Ao)))
+    its = max(abs(a.lastSolveIterations - b.lastSolveIterations) for a, b in zip(reps, oreps))
+    dts = max(abs(a.deltaT - b.deltaT) / b.deltaT for a, b in zip(reps, oreps))
+    ok = eT < 1e-9 and eA < 1e-9 and its <= 1 and dts < 1e-10
+    print(f"MULTI {mode} ranks={world} relLinf(T)={eT:.3e} Linf(alpha)={eA:.3e} iterdiff={its} dtdiff={dts:.2e} Tmax={To.max():.1f} "
+          f"{'OK' if ok else 'FAIL'}", flush=True)
+g.close(); ctx.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
