@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-nz", type=int, default=0, help="z layers of the CPU sample (0 = auto)")
-    ap.add_argument("--cpu-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=16)
     return ap.parse_args()
 
 
@@ -154,7 +154,8 @@ def main():
         print(json.dumps(line))
         return 0
 
-    import numpy as np
+    os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the one JSON line
+    import numpy as np  # noqa: F401
     import torch
     from additivefoam_b200 import abi, lib
 
@@ -238,6 +239,8 @@ def main():
 
     if rank != 0:
         g.close(); ctx.close()
+        dist.barrier()
+        dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel group (CUDA events around every launch, live in this run)
@@ -267,9 +270,9 @@ def main():
         cnz = args.cpu_sample_nz or max(8, min(cores, args.nz_per_gpu))
         ranks = min(cores, cnz)
         try:
-            r = run_cpu(args, cnz, args.cpu_steps, 1, ranks)
+            r = run_cpu(args, cnz, args.cpu_steps, args.warmup, ranks)
             cpu = {"value": r["value"], "unit": UNIT, "cores": ranks, "kind": "port",
-                   "sample": f"{args.nx}x{args.ny}x{cnz} cells ({cnz}/{args.nz_per_gpu} of the slab), {args.cpu_steps} steps after 1 warm-up, "
+                   "sample": f"{args.nx}x{args.ny}x{cnz} cells ({cnz}/{args.nz_per_gpu} of the slab), {args.cpu_steps} steps after {args.warmup} warm-up, "
                              f"{r['seconds']:.1f} s; restatement of the reference algorithm, not the OpenFOAM binary"}
         except Exception as e:     # the oracle is only the reported baseline
             cpu = {"value": None, "unit": UNIT, "cores": ranks, "kind": "port", "sample": f"failed: {e}"}
@@ -281,8 +284,11 @@ def main():
                        "cell_iterations_per_s": n_global * iters / (ms * 1e-3), "l2": "inputs larger than L2 (>= 100 MB per field)",
                        "last_step": last.as_dict()},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
     g.close(); ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
