@@ -1,6 +1,7 @@
 #include "ldu_kernels.cuh"
 #include "wave_kernels.cuh"
 #include <cstdlib>
+#include <set>
 #include "ctx.cuh"
 #include <algorithm>
 #include <cstring>
@@ -265,7 +266,7 @@ static WaveGeom wave_geom(const BlockDims& d)
     g.nx = d.nx; g.ny = d.ny; g.nz = d.nz;
     g.nJ = (d.ny + WTJ - 1) / WTJ; g.nK = (d.nz + WTK - 1) / WTK; g.nTiles = g.nJ * g.nK;
     g.nSteps = d.nx + WTJ + WTK - 2;
-    g.nStepsPad = (g.nSteps + 2 * WS - 1) / (2 * WS) * (2 * WS);      // an even number of WS-step groups
+    g.nStepsPad = (g.nSteps + 2 * GS - 1) / (2 * GS) * (2 * GS);      // an even number of GS-step (and WS-step) groups
     g.nxny = (int64_t)d.nx * d.ny;
     return g;
 }
@@ -295,10 +296,24 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
     // WF and WB for the substitution sweeps, which then re-arm each other's array as they go
     if (op == 0) B200_CUDA(cudaMemsetAsync(wave[8], 0xFF, (size_t)waveLen * sizeof(double), s));
     const int grid = a.g.nTiles;
-    if (op == 0) { if (dilu) k_wave<0, true, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false><<<grid, 32, 0, s>>>(a); }
-    else if (op == 1) k_wave<1, false, false><<<grid, 32, 0, s>>>(a);
-    else if (dot) k_wave<2, false, true><<<grid, 32, 0, s>>>(a);
-    else k_wave<2, false, false><<<grid, 32, 0, s>>>(a);
+    static const bool oneWarp = [] { const char* e = std::getenv("B200_WAVE"); return e && std::string(e) == "1warp"; }();
+    if (oneWarp) {
+        if (op == 0) { if (dilu) k_wave<0, true, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false><<<grid, 32, 0, s>>>(a); }
+        else if (op == 1) k_wave<1, false, false><<<grid, 32, 0, s>>>(a);
+        else if (dot) k_wave<2, false, true><<<grid, 32, 0, s>>>(a);
+        else k_wave<2, false, false><<<grid, 32, 0, s>>>(a);
+    } else {
+        auto launch = [&](auto kernel, size_t shm) {
+            static std::set<const void*> configured;     // every k_wave2 instantiation has the same pointer type
+            if (configured.insert((const void*)kernel).second)
+                B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            kernel<<<grid, 64, shm, s>>>(a);
+        };
+        if (op == 0) { if (dilu) launch(k_wave2<0, true, false>, sizeof(WaveSmem<0, true>)); else launch(k_wave2<0, false, false>, sizeof(WaveSmem<0, false>)); }
+        else if (op == 1) launch(k_wave2<1, false, false>, sizeof(WaveSmem<1, false>));
+        else if (dot) launch(k_wave2<2, false, true>, sizeof(WaveSmem<2, false>));
+        else launch(k_wave2<2, false, false>, sizeof(WaveSmem<2, false>));
+    }
     B200_LAUNCH_CHECK();
     if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }
 }
