@@ -296,7 +296,11 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
     // WF and WB for the substitution sweeps, which then re-arm each other's array as they go
     if (op == 0) B200_CUDA(cudaMemsetAsync(wave[8], 0xFF, (size_t)waveLen * sizeof(double), s));
     const int grid = a.g.nTiles;
-    static const bool oneWarp = [] { const char* e = std::getenv("B200_WAVE"); return e && std::string(e) == "1warp"; }();
+    // Two implementations of the same sweep (bit-identical results).  Few tiles (a thin slab: ~3 warps per SM) => the sweep
+    // is bound by the dependency chain and the warp-specialised kernel (memory warp + compute warp) is ahead; many tiles =>
+    // it is bound by HBM and the one-warp kernel, which keeps more tiles in flight per SM, is ahead.  B200_WAVE overrides.
+    static const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : 2; }();
+    const bool oneWarp = forced ? forced == 1 : a.g.nTiles > 1536;
     if (oneWarp) {
         if (op == 0) { if (dilu) k_wave<0, true, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false><<<grid, 32, 0, s>>>(a); }
         else if (op == 1) k_wave<1, false, false><<<grid, 32, 0, s>>>(a);
