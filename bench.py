@@ -119,6 +119,21 @@ def run_cpu(args, nz, steps, warmup, ranks):
     return dict(value=n * steps / dt, seconds=dt, cells=n, iterations=iters, steps=steps)
 
 
+def ncu_traffic(group, n_local):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's kernel from the committed ncu --set full capture
+    (profiles/r1_top_kernels_ncu_full.csv, taken on the default 12.8 M-cell slab); None for other sizes or groups."""
+    kern = {"sweep_fwd": "k_wave2<1", "sweep_bwd": "k_wave2<2", "factor": "k_wave2<0", "amul": "k_amul_block<2>"}.get(group)
+    path = os.path.join(ROOT, "profiles", "r1_top_kernels_ncu_full.csv")
+    if kern is None or n_local != 12800000 or not os.path.exists(path):
+        return None
+    import csv
+    rows = list(csv.reader(open(path)))
+    hdr = rows[0]
+    vals = [float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")]) for r in rows[1:]
+            if r and kern in r[0].replace("void ", "")]
+    return 1e6 * sum(vals) / len(vals) if vals else None      # the csv is in MB
+
+
 def peak_hbm():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -258,8 +273,9 @@ def main():
     shares = {k: round(v[0] / total_prof, 4) for k, v in prof.items() if v[1]}
     per_launch_ms = {k: v[0] / v[1] for k, v in prof.items() if v[1]}
     achieved = alg_bytes[dom] / (per_launch_ms[dom] * 1e-3) / 1e9
+    traffic = ncu_traffic(dom, nl)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
                 "avg_launch_ms": per_launch_ms[dom], "launches": prof[dom][1], "share_of_kernel_time": shares.get(dom),
                 "group_shares": shares,
                 "group_GBps": {k: round(alg_bytes[k] / (per_launch_ms[k] * 1e-3) / 1e9, 1) for k in per_launch_ms if alg_bytes.get(k)}}
