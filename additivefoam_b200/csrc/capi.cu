@@ -199,11 +199,9 @@ int b200_ldu_amul(b200_ldu* ldu, const double* diag, const double* upper, const 
     const double* d = stage_in(L, 0, diag, L.nCells);
     const double* u = stage_in(L, 1, upper, L.nFaces);
     const double* l = stage_in(L, 2, lower, L.nFaces);
-    // psi sits in the middle of its staging buffer so that block kernels may touch one plane either side
-    if (!L.stage[4]) L.stage[4] = dev_alloc<double>((size_t)3 * L.nCells + 16);
-    double* x = L.stage[4] + L.nCells;
-    h2d(x, psi, L.nCells, L.ctx->stream);
-    double* y = stage_in(L, 5, psi, L.nCells);
+    double* x = stage_in(L, 4, psi, L.nCells);
+    if (!L.stage[5]) L.stage[5] = dev_alloc<double>((size_t)L.nCells + 16);
+    double* y = L.stage[5];
     std::vector<const double*> bou = stage_bou(L, ifaceBouCoeffs);
     MatrixView A; A.diag = d; A.upper = u; A.lower = l ? l : u; A.bouCoeffs = bou.empty() ? nullptr : bou.data();
     L.amul(A, x, y);
@@ -222,6 +220,7 @@ int b200_ldu_precondition(b200_ldu* ldu, int32_t preconditioner, const double* d
     const double* u = stage_in(L, 1, upper, L.nFaces);
     const double* l = stage_in(L, 2, lower, L.nFaces);
     const double* r = stage_in(L, 3, rA, L.nCells);
+    // the wave sweeps never touch cells outside the block, but keep one plane of slack either side like the solver's vectors
     if (!L.stage[6]) L.stage[6] = dev_alloc<double>((size_t)3 * L.nCells + 16);
     double* w = L.stage[6] + L.nCells;
     MatrixView A; A.diag = d; A.upper = u; A.lower = l ? l : u;

@@ -196,7 +196,7 @@ void Ldu::exchange(const double* x)
     B200_NCCL(ncclGroupEnd());
 }
 
-void Ldu::allreduce(int slot0, int n, bool)
+void Ldu::allreduce(int slot0, int n)
 {
     if (ctx->nranks <= 1) return;
     ProfScope ps_(ctx, PC_COMM);

@@ -127,7 +127,7 @@ public:
     void applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int dotMode, const double* dotVec);
     void amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux);
     void exchange(const double* x);   // interface / ghost-plane update before an Amul on x
-    void allreduce(int slot0, int n, bool isMax = false);
+    void allreduce(int slot0, int n);
 };
 
 } // namespace b200

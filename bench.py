@@ -6,9 +6,11 @@
 
 A "step" is one full pass of additiveFoam's time-loop body (additiveFoam.C:66-95) over the whole block:
 properties, time-step control, moving heat source, TEqn assembly, every solidification corrector and every
-Krylov iteration.  Workload (weak scaling): BASELINE.json configs[2] family -- uniform 20 um hex block
-1000 x 400 x (32*N) cells, single superGaussian track, conduction + solidification, implicit PCG/DIC with the
-shipped solver controls (tolerance 1e-15, maxIter 20); N = 8 is the 102.4 M-cell case.
+Krylov iteration.  Workload: BASELINE.json configs[2] -- the synthetic 100 M-cell uniform-hex block (1000 x 400 x 250 cells of 20 um),
+single superGaussian track, conduction + solidification, implicit PCG/DIC with the shipped solver controls (tolerance
+1e-15, maxIter 20).  It fits one B200 (about 32 GB), so N = 1 runs exactly that case; N GPUs run N such z-slabs
+(weak scaling, 1000 x 400 x 250N cells).  `--nz-per-gpu 32` gives the thin-slab variant whose N = 8 run is the
+102.4 M-cell case of the BASELINE target (12.8 M cells per GPU).
 Prints ONE JSON line.
 """
 import argparse
@@ -34,7 +36,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=1000)
     ap.add_argument("--ny", type=int, default=400)
-    ap.add_argument("--nz-per-gpu", type=int, default=32)
+    ap.add_argument("--nz-per-gpu", type=int, default=250)
     ap.add_argument("--workload", default="track", choices=["track", "rosenthal"])
     ap.add_argument("--solver", default="PCG", choices=["PCG", "PBiCGStab"])
     ap.add_argument("--preconditioner", default="DIC", choices=["DIC", "DILU", "diagonal", "none"])
@@ -59,7 +61,8 @@ def make_case(args, nz, pre_steps_dt=2e-5):
 def workload_name(args, nz):
     kind = "conduction-only Rosenthal track" if args.workload == "rosenthal" else "conduction+solidification track"
     return (f"synthetic uniform-hex {args.nx}x{args.ny}x{nz} cells (20 um), single superGaussian beam, {kind}, implicit "
-            f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20 (BASELINE configs[2] family; {args.nz_per_gpu} z-layers per GPU)")
+            f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20 (BASELINE configs[2]: 100 M cells per GPU slab of "
+            f"{args.nz_per_gpu} z-layers; weak scaling over z-slabs)")
 
 
 class ClockSampler(threading.Thread):
@@ -122,15 +125,15 @@ def run_cpu(args, nz, steps, warmup, ranks):
 def ncu_traffic(group, n_local):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's kernel from the committed ncu --set full capture
     (profiles/r1_top_kernels_ncu_full.csv, taken on the default 12.8 M-cell slab); None for other sizes or groups."""
-    kern = {"sweep_fwd": "k_wave2<1", "sweep_bwd": "k_wave2<2", "factor": "k_wave2<0", "amul": "k_amul_block<2>"}.get(group)
-    path = os.path.join(ROOT, "profiles", "r1_top_kernels_ncu_full.csv")
-    if kern is None or n_local != 12800000 or not os.path.exists(path):
+    tag = {"sweep_fwd": "<1,", "sweep_bwd": "<2,", "factor": "<0,", "amul": "k_amul_block<2>"}.get(group)
+    path = os.path.join(ROOT, "profiles", f"r1_top_kernels_ncu_full_{n_local}.csv")
+    if tag is None or not os.path.exists(path):
         return None
     import csv
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
     vals = [float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")]) for r in rows[1:]
-            if r and kern in r[0].replace("void ", "")]
+            if r and tag in r[0] and ("k_wave" in r[0] or "k_amul" in r[0])]
     return 1e6 * sum(vals) / len(vals) if vals else None      # the csv is in MB
 
 
