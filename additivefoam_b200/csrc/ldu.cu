@@ -290,6 +290,15 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
     a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12];
     a.rA = rA; a.wA = wA;
     a.ticket = waveFlags; a.tilePartial = wavePartial; a.st = d_state;
+    {
+        // keep what the resident tiles have prefetched but not yet consumed well inside L2 (126 MB): about 32 MB in flight
+        const int64_t resident = std::min<int64_t>(a.g.nTiles, (int64_t)ctx->smCount * 12);
+        const int64_t perGroup = resident * 5 * WS * 32 * (int64_t)sizeof(double);
+        int pf = (int)((32ll << 20) / std::max<int64_t>(perGroup, 1));
+        pf = std::min(12, pf / 4 * 4);
+        static const char* e = std::getenv("B200_WAVE_PF");
+        a.pfGroups = e ? std::atoi(e) : pf;
+    }
     cudaStream_t s = ctx->stream;
     B200_CUDA(cudaMemsetAsync(waveFlags, 0, sizeof(int), s));
     // the factor sweep exchanges raw rD through RF: arm it with the sentinel (all-ones NaN); the factor sweep itself arms
@@ -420,14 +429,18 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     }
     std::memset(h_state, 0, sizeof(SolveState));
     h_state->tol = sc.tolerance; h_state->relTol = sc.relTol; h_state->minIter = sc.minIter; h_state->maxIter = sc.maxIter;
-    double nGlobal = (double)n;
-    if (ctx->nranks > 1) {
-        // global cell count for gAverage(psi): one tiny allreduce per solve
-        B200_CUDA(cudaMemcpyAsync(red.result + S_NSLOTS - 1, &nGlobal, sizeof(double), cudaMemcpyHostToDevice, s));
-        ctx->allreduceSum(red.result + S_NSLOTS - 1, 1);
-        B200_CUDA(cudaMemcpyAsync(&nGlobal, red.result + S_NSLOTS - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
-        ctx->sync();
+    if (nGlobalCells < 0) {
+        // global cell count for gAverage(psi): one tiny allreduce, once per addressing
+        double nGlobal = (double)n;
+        if (ctx->nranks > 1) {
+            B200_CUDA(cudaMemcpyAsync(red.result + S_NSLOTS - 1, &nGlobal, sizeof(double), cudaMemcpyHostToDevice, s));
+            ctx->allreduceSum(red.result + S_NSLOTS - 1, 1);
+            B200_CUDA(cudaMemcpyAsync(&nGlobal, red.result + S_NSLOTS - 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+            ctx->sync();
+        }
+        nGlobalCells = nGlobal;
     }
+    const double nGlobal = nGlobalCells;
     h_state->nGlobal = nGlobal;
     h2d(d_state, h_state, 1, s);
     const SolveState* st = d_state;

@@ -102,6 +102,7 @@ public:
     double* stage[8] = {nullptr};    // device staging of host-pointer calls (b200_ldu_solve)
     std::vector<double*> stageBou;
     int nLevels = 0, maxLevelSize = 0;
+    double nGlobalCells = -1;        // cells over all ranks (cached)
     std::vector<int> h_lower, h_upper;
     std::vector<DevInterface> ifaces;
     // work vectors (device), allocated on first solve; each has one ghost plane either side in block mode

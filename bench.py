@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--ny", type=int, default=400)
     ap.add_argument("--nz-per-gpu", type=int, default=250)
     ap.add_argument("--workload", default="track", choices=["track", "rosenthal"])
+    ap.add_argument("--explicit", action="store_true", help="as-shipped mode of configs[0]: explicitSolve true, maxDi 1 (diagonal solves only)")
     ap.add_argument("--solver", default="PCG", choices=["PCG", "PBiCGStab"])
     ap.add_argument("--preconditioner", default="DIC", choices=["DIC", "DILU", "diagonal", "none"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -53,6 +54,8 @@ def make_case(args, nz, pre_steps_dt=2e-5):
     precond = dict(DIC=abi.PRECOND_DIC, DILU=abi.PRECOND_DILU, diagonal=abi.PRECOND_DIAGONAL, none=abi.PRECOND_NONE)[args.preconditioner]
     n = (args.nx, args.ny, nz)
     ctl = dict(solver=solver, preconditioner=precond, deltaT=pre_steps_dt, explicitSolve=0, maxDi=10.0)
+    if args.explicit:
+        ctl.update(explicitSolve=1, maxDi=1.0, deltaT=2e-6)
     if args.workload == "rosenthal":
         return cases.rosenthal(n, **ctl)
     return cases.synthetic_track(n, **ctl)
@@ -60,6 +63,8 @@ def make_case(args, nz, pre_steps_dt=2e-5):
 
 def workload_name(args, nz):
     kind = "conduction-only Rosenthal track" if args.workload == "rosenthal" else "conduction+solidification track"
+    if args.explicit:
+        kind += ", explicitSolve true / maxDi 1 (as-shipped mode)"
     return (f"synthetic uniform-hex {args.nx}x{args.ny}x{nz} cells (20 um), single superGaussian beam, {kind}, implicit "
             f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20 (BASELINE configs[2]: 100 M cells per GPU slab of "
             f"{args.nz_per_gpu} z-layers; weak scaling over z-slabs)")
@@ -132,9 +137,9 @@ def ncu_traffic(group, n_local):
     import csv
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
-    vals = [float(r[hdr.index("dram__bytes_read.sum")]) + float(r[hdr.index("dram__bytes_write.sum")]) for r in rows[1:]
+    vals = [float(r[hdr.index("dram_read_bytes")]) + float(r[hdr.index("dram_write_bytes")]) for r in rows[1:]
             if r and tag in r[0] and ("k_wave" in r[0] or "k_amul" in r[0])]
-    return 1e6 * sum(vals) / len(vals) if vals else None      # the csv is in MB
+    return sum(vals) / len(vals) if vals else None
 
 
 def peak_hbm():
