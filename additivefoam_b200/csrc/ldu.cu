@@ -346,17 +346,23 @@ void Ldu::factor(int kind, const MatrixView& A)
         const double* nul = nullptr; double* nulw = nullptr;
         if (isBlock && useWave) {
             ensureWave(dilu);
-            WaveArgs a;
-            a.g = wave_geom(dims);
-            a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
-            a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.st = st;
-            const int64_t rows = (int64_t)a.g.nTiles * a.g.nStepsPad;
-            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->smCount * 16));
-            if (dilu) k_wave_gather<true><<<grid, 256, 0, s>>>(dims, a, A.diag, A.upper, A.lower);
-            else k_wave_gather<false><<<grid, 256, 0, s>>>(dims, a, A.diag, A.upper, A.lower);
-            B200_LAUNCH_CHECK();
-            waveSweep(0, dilu, false, nullptr, nullptr);
-            return;          // rD lives in wave order (A0); P*, Q* are already scaled by it
+            // the unscaled wave-order coefficients depend on the off-diagonals only: regather when they may have changed
+            const bool same = A.offDiagEpoch >= 0 && A.offDiagEpoch == waveEpoch && A.upper == waveUpper && A.lower == waveLower
+                           && dilu == waveDilu;
+            if (!same) {
+                WaveArgs a;
+                a.g = wave_geom(dims);
+                a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
+                a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.st = st;
+                const int64_t rows = (int64_t)a.g.nTiles * a.g.nStepsPad;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->smCount * 16));
+                if (dilu) k_wave_gather<true><<<grid, 256, 0, s>>>(dims, a, A.upper, A.lower);
+                else k_wave_gather<false><<<grid, 256, 0, s>>>(dims, a, A.upper, A.lower);
+                B200_LAUNCH_CHECK();
+                waveEpoch = A.offDiagEpoch; waveUpper = A.upper; waveLower = A.lower; waveDilu = dilu;
+            }
+            waveSweep(0, dilu, false, A.diag, nullptr);
+            return;          // rD lives in wave order (A0)
         } else if (isBlock) {
             if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
             else coop_launch(ctx, k_sweep_block<0, false, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);

@@ -50,6 +50,9 @@ struct MatrixView {
     const double* upper = nullptr;
     const double* lower = nullptr;                 // == upper when symmetric
     const double* const* bouCoeffs = nullptr;      // host array of device pointers, one per interface
+    // >= 0: the caller promises that upper/lower are unchanged since its last solve with the same value (the resident
+    // stepper assembles the off-diagonals once per time step and solves once per corrector); -1: assume they changed
+    int offDiagEpoch = -1;
     bool asymmetric() const { return lower != upper; }
 };
 
@@ -119,6 +122,7 @@ public:
     int* waveFlags = nullptr;        // tile ticket
     double* wavePartial = nullptr;
     int64_t waveLen = 0;
+    int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
     void ensureWave(bool dilu);
     void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA);
 

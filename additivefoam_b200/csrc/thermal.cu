@@ -430,6 +430,7 @@ void ThermalCase::step(b200_step_report* rep)
     sc.solver = ctl.solver; sc.precond = ctl.preconditioner; sc.tolerance = ctl.tolerance; sc.relTol = ctl.relTol;
     sc.minIter = ctl.minIter; sc.maxIter = ctl.maxIter;
     MatrixView A; A.diag = diag; A.upper = upper; A.lower = upper; A.bouCoeffs = bouPtrs;
+    A.offDiagEpoch = timeIndex;            // the off-diagonals are assembled once per time step (thermoScheme.H)
     SolvePerf perf;
     int nCorrDone = 0, iterSum = 0;
     double residual = 0;
