@@ -78,8 +78,10 @@ Ldu::Ldu(Ctx* c, int nCells_, int nFaces_, const int* lower, const int* upper, i
     h2d(d_rowStart, rowStart.data(), nCells + 1, s); h2d(d_rowMid, rowMid.data(), nCells, s);
     h2d(d_rowCol, rowCol.data(), rowCol.size(), s); h2d(d_rowFace, rowFace.data(), rowFace.size(), s);
     h2d(d_lvlCells, lvlCells.data(), nCells, s); h2d(d_lvlStart, h_lvlStart.data(), nLevels + 1, s);
+    B200_CHECK(nInterfaces == 0 || ctx->nranks > 1, "coupled interfaces need a multi-rank context (b200_ctx_create with nranks > 1)");
     for (int p = 0; p < nInterfaces; p++) {
         DevInterface it;
+        B200_CHECK(ifaceNeighbRank[p] >= 0 && ifaceNeighbRank[p] < ctx->nranks && ifaceNeighbRank[p] != ctx->rank, "interface neighbour rank out of range");
         it.size = ifaceSize[p]; it.neighbRank = ifaceNeighbRank[p];
         it.faceCells = dev_alloc<int>(it.size);
         h2d(it.faceCells, ifaceFaceCells[p], it.size, s);
@@ -123,6 +125,8 @@ void Ldu::setBlock(int nx, int ny, int nz)
     BlockDims d; d.nx = nx; d.ny = ny; d.nz = nz;
     B200_CHECK(nx > 0 && ny > 0 && nz > 0, "block dimensions must be positive");
     B200_CHECK(d.nCells() == nCells && d.nFaces() == nFaces, "block dimensions do not match nCells/nFaces");
+    B200_CHECK(ifaces.empty(), "the block kernels take their coupled neighbours from ghost planes (resident stepper); a decomposed "
+                               "OpenFOAM mesh keeps the general addressing path");
     // expand the closed form on the device and compare bit-exactly with the addressing given at creation
     int* lo = dev_alloc<int>(nFaces); int* up = dev_alloc<int>(nFaces);
     k_block_addressing<<<std::min(ny * nz, 4096), BLK, 0, ctx->stream>>>(d, lo, up);

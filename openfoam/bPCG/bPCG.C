@@ -111,6 +111,15 @@ b200_ldu* Foam::b200SolverBase::handle() const
         ),
         "b200_ldu_create"
     );
+    // optional: `blockNx/blockNy/blockNz` in the solver dictionary declares a single blockMesh hex block (serial runs); the
+    // library verifies the addressing bit-exactly and switches to its addressing-free kernels
+    const label bnx = controlDict_.lookupOrDefault<label>("blockNx", 0);
+    const label bny = controlDict_.lookupOrDefault<label>("blockNy", 0);
+    const label bnz = controlDict_.lookupOrDefault<label>("blockNz", 0);
+    if (bnx > 0 && bny > 0 && bnz > 0 && !Pstream::parRun())
+    {
+        b200Check(b200_ldu_set_block(h, bnx, bny, bnz), "b200_ldu_set_block");
+    }
     cache[&addr] = h;
     return h;
 }
