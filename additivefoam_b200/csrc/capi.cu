@@ -48,6 +48,20 @@ int b200_ctx_destroy(b200_ctx* ctx)
     if (ctx) { delete ctx->p; delete ctx; }
     B200_CATCH
 }
+int b200_ctx_peer_export(b200_ctx* ctx, void* handle64)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    ctx->p->peerExport(handle64);
+    B200_CATCH
+}
+int b200_ctx_peer_import(b200_ctx* ctx, const void* handles)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    ctx->p->peerImport(handles);
+    B200_CATCH
+}
 int b200_ctx_synchronize(b200_ctx* ctx)
 {
     B200_TRY

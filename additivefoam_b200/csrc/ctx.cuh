@@ -19,8 +19,25 @@ enum ProfCat { PC_AMUL = 0, PC_SWEEP_FWD, PC_SWEEP_BWD, PC_FACTOR, PC_VECTOR, PC
                PC_ASSEMBLE, PC_CORRECTOR, PC_ALPHA, PC_BOUNDARY, PC_QDOT, PC_COPY, PC_COMM, PC_NCAT };
 const char* prof_name(int cat);
 
+// Peer-memory mailbox of the small all-reduces (Krylov dot products, residual norms, time-step numbers): every rank stores
+// its partial into every peer's mailbox over NVLink and sums the R partials in rank order itself -- one short kernel, no
+// library call, bitwise the same result on every rank.
+constexpr int PEER_MAX_RANKS = 16, PEER_RING = 4, PEER_VALS = 8;
+struct PeerMail {
+    double val[PEER_RING][PEER_MAX_RANKS][PEER_VALS];
+    unsigned long long flag[PEER_RING][PEER_MAX_RANKS];
+};
+struct PeerPtrs { PeerMail* p[PEER_MAX_RANKS]; };
+
 struct Ctx {
     int device = 0, rank = 0, nranks = 1;
+    PeerMail* myMail = nullptr;
+    PeerPtrs peers{};
+    bool peerOK = false;
+    unsigned long long peerSeq = 0;
+    void peerExport(void* handle64);
+    void peerImport(const void* handles);     // nranks x 64 bytes, rank order
+    void allreduce(double* buf, int n, int op);   // op: 0 sum, 1 max, 2 min
     // profiler: one event pair per instrumented launch group, resolved at read time
     bool profOn = false;
     struct ProfRec { int cat; cudaEvent_t a, b; };

@@ -24,7 +24,7 @@ dp, ip = abi.c_double_p, abi.c_int32_p
 #: every symbol include/additivefoam_b200.h declares
 SYMBOLS = [
     "b200_last_error", "b200_abi_version", "b200_nccl_unique_id", "b200_ctx_create", "b200_ctx_destroy",
-    "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
+    "b200_ctx_peer_export", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
@@ -74,6 +74,8 @@ def load():
     L.b200_ctx_create.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.POINTER(vp)]
     L.b200_ctx_destroy.argtypes = [vp]
     L.b200_ctx_synchronize.argtypes = [vp]
+    L.b200_ctx_peer_export.argtypes = [vp, vp]
+    L.b200_ctx_peer_import.argtypes = [vp, vp]
     L.b200_ctx_mark.argtypes = [vp, C.c_int]
     L.b200_ctx_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     L.b200_profile_enable.argtypes = [vp, C.c_int]
@@ -142,6 +144,17 @@ class Context:
 
     def synchronize(self):
         _check(self.L.b200_ctx_synchronize(self.h))
+
+    def peer_export(self):
+        """64-byte IPC handle of this rank's all-reduce mailbox."""
+        buf = (C.c_char * 64)()
+        _check(self.L.b200_ctx_peer_export(self.h, buf))
+        return bytes(buf)
+
+    def peer_import(self, handles):
+        """`handles`: the 64-byte handles of all ranks, concatenated in rank order."""
+        assert len(handles) == 64 * self.nranks
+        _check(self.L.b200_ctx_peer_import(self.h, C.create_string_buffer(handles, len(handles))))
 
     def mark(self, i):
         """Record CUDA event ``i`` (0..3) on the library's stream."""

@@ -45,3 +45,13 @@ def max_over_ranks(value, dist, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def enable_peer_allreduce(ctx, dist, device=None):
+    """All ranks of one node: exchange the IPC handles of the all-reduce mailboxes and switch the library's scalar
+    all-reduces from NCCL to the NVLink peer-memory exchange."""
+    import torch
+    mine = torch.tensor(list(ctx.peer_export()), dtype=torch.uint8, device=device)
+    out = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(ctx.nranks)]
+    dist.all_gather(out, mine)
+    ctx.peer_import(b"".join(bytes(o.cpu().tolist()) for o in out))

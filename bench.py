@@ -193,6 +193,9 @@ def main():
         dist.broadcast(t, 0)
         uid = bytes(t.cpu().tolist())
     ctx = lib.Context(local, uid, rank, world)
+    if world > 1 and os.environ.get("B200_PEER_ALLREDUCE", "1") != "0":
+        from additivefoam_b200 import partition
+        partition.enable_peer_allreduce(ctx, dist, device="cuda")
     nz = args.nz_per_gpu * world
     case = make_case(args, nz)
     g = lib.Case(ctx, case)

@@ -173,6 +173,10 @@ int  b200_abi_version(void);
 int  b200_nccl_unique_id(void* out128);
 int  b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, int nranks, b200_ctx** out);
 int  b200_ctx_destroy(b200_ctx* ctx);
+/* Optional, ranks of one node: replace the NCCL all-reduces of scalars by a peer-memory (NVLink) mailbox exchange.
+ * Every rank exports a 64-byte cudaIpcMemHandle_t, the host gathers them in rank order, every rank imports the list. */
+int  b200_ctx_peer_export(b200_ctx* ctx, void* handle64);
+int  b200_ctx_peer_import(b200_ctx* ctx, const void* handles /* nranks x 64 bytes */);
 int  b200_ctx_synchronize(b200_ctx* ctx);
 /* CUDA events on the library's own stream (bench.py times the step with these): record mark i (0..3);
  * elapsed ms between two recorded marks (synchronises). */

@@ -19,6 +19,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 uid = partition.broadcast_unique_id(lib.nccl_unique_id, rank, dist, device="cuda")
 ctx = lib.Context(local, uid, rank, world)
+if os.environ.get("B200_PEER_ALLREDUCE", "1") != "0":
+    partition.enable_peer_allreduce(ctx, dist, device="cuda")
 n = (48, 14, 11)
 kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC) if mode == "implicit" else dict()
 if mode == "bicg":
