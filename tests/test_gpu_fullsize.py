@@ -69,3 +69,14 @@ def test_solve_residual_property_3m(ctx, oracle):
     assert np.abs(b - Ax).sum() / nfac == pytest.approx(perf.finalResidual, rel=1e-6)
     assert perf.finalResidual < 1e-9
     s.close()
+
+
+def test_rosenthal_analytic_gpu(ctx):
+    """The same analytic pin through the C ABI (b200_case_*)."""
+    import rosenthal
+    case = rosenthal.case()
+    g = lib.Case(ctx, case)
+    while g.running():
+        r = g.step()
+    rosenthal.check(rosenthal.compare(g.field(abi.FIELD_T), r.time, case["mesh"]))
+    g.close()

@@ -322,3 +322,14 @@ def test_melt_pool_forms_and_solidifies(oracle):
     a = c.field(abi.FIELD_ALPHA_SOLID)
     assert minA < 0.5 and a.min() >= 0.0 and a.max() <= 1.0
     c.close()
+
+
+def test_rosenthal_analytic(oracle):
+    """An oracle-independent pin of the conduction path: the moving-source field against Rosenthal's solution."""
+    import rosenthal
+    case = rosenthal.case()
+    c = ol.OracleCase(case, ranks=5, lib=oracle)
+    while c.running():
+        r = c.step()
+    rosenthal.check(rosenthal.compare(c.field(abi.FIELD_T), r.time, case["mesh"]))
+    c.close()
