@@ -301,6 +301,13 @@ int b200_case_set_field(b200_case* c, int32_t field, const double* in)
     c->p->setField(field, in);
     B200_CATCH
 }
+int b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* isoValues, double scanPathAngleDeg, double* dims)
+{
+    B200_TRY
+    B200_CHECK(c && nIso >= 0 && (nIso == 0 || (isoValues && dims)), "melt_pool_dimensions: bad arguments");
+    c->p->meltPoolDimensions(nIso, isoValues, scanPathAngleDeg, dims);
+    B200_CATCH
+}
 int b200_case_kernel_launches(b200_case*, int64_t* launches)
 {
     *launches = g_launches;

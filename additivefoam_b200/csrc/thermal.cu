@@ -196,6 +196,23 @@ void ThermalCase::setField(int fIn, const double* in)
     ctx->sync();
 }
 
+// functionObjects/meltPoolDimensions: dims[3*i..] = max(span, 0) of isotherm i in the scan-path frame; the field never leaves HBM
+void ThermalCase::meltPoolDimensions(int nIso, const double* isoValues, double scanPathAngleDeg, double* out)
+{
+    const double radians = scanPathAngleDeg * (3.14159265358979323846 / 180.0);
+    const double sn = std::sin(radians), cs = std::cos(radians);
+    haloExchange(T);
+    for (int q = 0; q < nIso; q++) {
+        k_melt_pool<<<cells_grid(ctx, dims), BLK, 0, ctx->stream>>>(dims, geo, sidesDev, T, isoValues[q], cs, sn, red);
+        B200_LAUNCH_CHECK();
+        ctx->allreduceMin(red.result + R_MPOOL, 3);
+        ctx->allreduceMax(red.result + R_MPOOL + 3, 3);
+        d2h(h_red + R_MPOOL, red.result + R_MPOOL, 6, ctx->stream);
+        ctx->sync();
+        for (int a = 0; a < 3; a++) out[3 * q + a] = std::max(h_red[R_MPOOL + 3 + a] - h_red[R_MPOOL + a], 0.0);
+    }
+}
+
 void ThermalCase::haloExchange(double* f)
 {
     if (ctx->nranks <= 1) return;

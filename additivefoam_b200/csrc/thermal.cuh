@@ -56,6 +56,7 @@ public:
     int64_t nGlobal() const { return (int64_t)dims.nx * dims.ny * nzGlobal; }
     void getField(int field, double* out);
     void setField(int field, const double* in);
+    void meltPoolDimensions(int nIso, const double* isoValues, double scanPathAngleDeg, double* dims);
 
     Ctx* ctx;
 private:

@@ -7,7 +7,7 @@
 
 namespace b200 {
 
-enum { R_ALPHACO = 0, R_MINALPHA = 1, R_DIMAX = 2, R_POWER = 3, R_RESID = 4, R_SUMW = 5, R_DEPTH = 6, R_VOLUME = 7, R_NSLOTS = 16 };
+enum { R_ALPHACO = 0, R_MINALPHA = 1, R_DIMAX = 2, R_POWER = 3, R_RESID = 4, R_SUMW = 5, R_DEPTH = 6, R_VOLUME = 7, R_MPOOL = 8 /* 6 slots */, R_NSLOTS = 16 };
 
 struct MatDev {
     double kappa[3][3], Cp[3][3], rho, Lf, Tliq, Tsol;
@@ -377,6 +377,64 @@ __global__ void __launch_bounds__(BLK) k_fill(int64_t n, double* __restrict__ a,
 __global__ void __launch_bounds__(BLK) k_reciprocal_of(int64_t n, const double* __restrict__ a, double* __restrict__ b)
 {
     for (int64_t c = blockIdx.x * (int64_t)BLK + threadIdx.x; c < n; c += (int64_t)gridDim.x * BLK) b[c] = 1.0 / a[c];
+}
+
+// functionObjects/meltPoolDimensions/meltPoolDimensions.C:123-294 for one isovalue: bounding box (in the frame rotated by the
+// scan path angle) of the isotherm located linearly between cell centres across internal and processor faces, plus the face centres
+// of physical boundary faces whose cell or patch value reaches the isovalue.  Six min/max reductions -> red.result[R_MPOOL..+5].
+__global__ void __launch_bounds__(BLK) k_melt_pool(BlockDims d, Geom g, SidesDev sd, const double* __restrict__ T, double iso, double cs,
+                                                   double sn, RedWork red)
+{
+    const int nx = d.nx; const int64_t nxny = (int64_t)d.nx * d.ny;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    auto add = [&](double x, double y, double z) {
+        const double qx = x * cs + y * sn, qy = y * cs - x * sn;
+        lo[0] = fmin(qx, lo[0]); lo[1] = fmin(qy, lo[1]); lo[2] = fmin(z, lo[2]);
+        hi[0] = fmax(qx, hi[0]); hi[1] = fmax(qy, hi[1]); hi[2] = fmax(z, hi[2]);
+    };
+    B200_FOR_CELLS(d)
+    {
+        B200_CELL_INDEX(d)
+        const double To = T[c];
+        const double cx = g.ox + (i + 0.5) * g.dx, cy = g.oy + (j + 0.5) * g.dy, cz = g.oz + (k + g.k0 + 0.5) * g.dz;
+        auto cross = [&](double Tn, double nx_, double ny_, double nz_) {
+            if (fmin(To, Tn) < iso && fmax(To, Tn) >= iso) {
+                const double fr = iso - To, den = Tn - To;
+                add(cx + (nx_ - cx) * fr / den, cy + (ny_ - cy) * fr / den, cz + (nz_ - cz) * fr / den);
+            }
+        };
+        if (i < nx - 1) cross(T[c + 1], g.ox + (i + 1.5) * g.dx, cy, cz);
+        if (j < d.ny - 1) cross(T[c + nx], cx, g.oy + (j + 1.5) * g.dy, cz);
+        if (k < d.nz - 1) cross(T[c + nxny], cx, cy, g.oz + (k + g.k0 + 1.5) * g.dz);
+        const bool bnd = i == 0 || i == nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
+        for (int s = 0; bnd && s < 6; s++) {
+            if (!on_side(d, s, i, j, k)) continue;
+            const int type = sd.type[s];
+            if (type == SIDE_PROCESSOR) {
+                // both ranks treat their own patch face with themselves as the owner side
+                if (s == B200_ZMIN) cross(T[c - nxny], cx, cy, g.oz + (k + g.k0 - 0.5) * g.dz);
+                else cross(T[c + nxny], cx, cy, g.oz + (k + g.k0 + 1.5) * g.dz);
+                continue;
+            }
+            const double Tb = type == B200_BC_ZERO_GRADIENT ? To : sd.Tb[s][side_index(d, s, i, j, k)];
+            if (fmax(To, Tb) >= iso) {
+                double fx = cx, fy = cy, fz = cz;
+                switch (s) {
+                case B200_XMIN: fx = g.ox + 0 * g.dx; break;
+                case B200_XMAX: fx = g.ox + nx * g.dx; break;
+                case B200_YMIN: fy = g.oy + 0 * g.dy; break;
+                case B200_YMAX: fy = g.oy + d.ny * g.dy; break;
+                case B200_ZMIN: fz = g.oz + (0 + g.k0) * g.dz; break;
+                default: fz = g.oz + (d.nz + g.k0) * g.dz; break;
+                }
+                add(fx, fy, fz);
+            }
+        }
+    }
+    __shared__ double smem[32];
+    double v[6] = {lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]};
+    const int ops[6] = {2, 2, 2, 1, 1, 1};
+    grid_reduce<6>(v, ops, red, R_MPOOL, smem);
 }
 
 } // namespace b200

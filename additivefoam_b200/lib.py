@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
-    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_kernel_launches",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_kernel_launches",
     "b200_scan_path_parse",
 ]
 
@@ -101,6 +101,7 @@ def load():
     L.b200_case_n_cells.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.b200_case_get_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_set_field.argtypes = [vp, C.c_int32, dp]
+    L.b200_case_melt_pool_dimensions.argtypes = [vp, C.c_int32, dp, C.c_double, dp]
     L.b200_case_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.b200_scan_path_parse.argtypes = [C.c_char_p, dp, C.c_int32]
     _lib = L
@@ -294,6 +295,13 @@ class Case:
     def set_field_keep_old(self, f, a):
         """set_field without touching the old-time copy (host application owns the field between steps)."""
         _check(self.L.b200_case_set_field(self.h, f | 0x100, _P(a)))
+
+    def melt_pool_dimensions(self, iso_values, angle_deg=0.0):
+        """meltPoolDimensions function object (meltPoolDimensions.C:123-294): (nIso, 3) spans, computed on the device."""
+        iso = np.ascontiguousarray(iso_values, dtype=np.float64)
+        out = np.empty(3 * len(iso))
+        _check(self.L.b200_case_melt_pool_dimensions(self.h, len(iso), _P(iso), float(angle_deg), _P(out)))
+        return out.reshape(-1, 3)
 
     def close(self):
         if self.h:

@@ -244,6 +244,12 @@ int  b200_case_step(b200_case* c, b200_step_report* report);
 int  b200_case_n_cells(b200_case* c, int64_t* nLocal, int64_t* nGlobal);
 int  b200_case_get_field(b200_case* c, int32_t field, double* out);
 int  b200_case_set_field(b200_case* c, int32_t field, const double* in);
+/* functionObjects/meltPoolDimensions/meltPoolDimensions.C:123-294 evaluated on the device-resident T (no D2H of the field):
+ * for each isoValue the bounding box, in the frame rotated about z by scanPathAngle (degrees), of the isotherm located linearly
+ * between cell centres across internal and processor faces plus the centres of physical boundary faces whose cell or patch value
+ * reaches it; dims[3*i+0..2] = max(span, 0) in x, y, z -- the three numbers the reference logs per isoValue (:283-291).
+ * Collective over the ranks of the context. */
+int  b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* isoValues, double scanPathAngleDeg, double* dims);
 /* Device time (ms) spent in the kernels of the last step by group, for the benchmark:
  * [0] properties+dt numbers, [1] heat source, [2] assembly, [3] corrector fold+alpha update,
  * [4] Krylov solve. */

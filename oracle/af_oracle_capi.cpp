@@ -254,6 +254,14 @@ int afo_case_assemble_probe(void* h, int explicitSolve, scalar* diag, scalar* up
     std::memcpy(source, s.source.data(), sizeof(scalar) * s.source.size());
     return 0;
 }
+int afo_case_melt_pool_dimensions(void* h, label nIso, const scalar* iso, scalar angleDeg, scalar* dims)
+{
+    std::vector<scalar> v(iso, iso + nIso);
+    std::vector<Vec3> out;
+    ((Case*)h)->meltPoolDimensions(v, angleDeg, out);
+    for (label i = 0; i < nIso; i++) { dims[3 * i] = out[i].x; dims[3 * i + 1] = out[i].y; dims[3 * i + 2] = out[i].z; }
+    return 0;
+}
 scalar afo_case_time(void* h) { return ((Case*)h)->time; }
 scalar afo_case_Tliq(void* h) { return ((Case*)h)->Tliq; }
 scalar afo_case_Tsol(void* h) { return ((Case*)h)->Tsol; }

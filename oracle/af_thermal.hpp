@@ -209,6 +209,7 @@ struct Case {
     void assembleBase(bool explicitSolve);
     void thermoSource(int r);
     SolverPerf solveCorrector(bool explicitSolve, scalar rDeltaT, scalar rDeltaTEuler);
+    void meltPoolDimensions(const std::vector<scalar>& isoValues, scalar scanPathAngleDeg, std::vector<Vec3>& dims);
 };
 
 // ---------------------------------------------------------------------------------------
@@ -670,6 +671,84 @@ inline SolverPerf Case::solveCorrector(bool explicitSolve, scalar rDeltaT, scala
     forRanks(R, [&](int r) { rk[r].T = psi[r]; });
     forRanks(R, [&](int r) { correctTBoundary(r); });
     return perf;
+}
+
+// SOLVER/functionObjects/meltPoolDimensions/meltPoolDimensions.C:123-294 (a "next" row): bounding box of each
+// isotherm, located linearly between cell centres across internal and processor faces, plus the face centres of physical
+// boundary faces whose cell or patch value reaches the isovalue; rotated by the scan path angle.
+inline void Case::meltPoolDimensions(const std::vector<scalar>& isoValues, scalar scanPathAngleDeg, std::vector<Vec3>& dims)
+{
+    const scalar radians = scanPathAngleDeg * (pi_ / 180.0);
+    const scalar sn = std::sin(radians), cs = std::cos(radians);
+    const size_t nIso = isoValues.size();
+    std::vector<Vec3> bmin(nIso, Vec3{vGreat, vGreat, vGreat}), bmax(nIso, Vec3{-vGreat, -vGreat, -vGreat});
+    auto add = [&](size_t i, Vec3 p) {
+        const Vec3 q{p.x * cs + p.y * sn, p.y * cs - p.x * sn, p.z};
+        bmin[i] = {std::min(q.x, bmin[i].x), std::min(q.y, bmin[i].y), std::min(q.z, bmin[i].z)};
+        bmax[i] = {std::max(q.x, bmax[i].x), std::max(q.y, bmax[i].y), std::max(q.z, bmax[i].z)};
+    };
+    for (int r = 0; r < R; r++) {
+        const RankState& s = rk[r];
+        const Mesh& m = s.mesh;
+        auto cross = [&](scalar To, scalar Tn, Vec3 co, Vec3 cn) {
+            const scalar minFace = std::min(To, Tn), maxFace = std::max(To, Tn);
+            for (size_t i = 0; i < nIso; i++) {
+                const scalar iso = isoValues[i];
+                if (minFace < iso && maxFace >= iso) add(i, co + (cn - co) * (iso - To) / (Tn - To));
+            }
+        };
+        for (label f = 0; f < m.addr.nFaces; f++) {
+            const label own = m.addr.lower[f], nei = m.addr.upper[f];
+            cross(s.T[own], s.T[nei], m.C(own), m.C(nei));
+        }
+        for (const Patch& p : m.patches) {
+            if (p.type == PROCESSOR) {
+                const Interface& itf = m.interfaces[p.ifaceIndex];
+                const RankState& sn_ = rk[itf.neighbRank];
+                for (size_t i = 0; i < p.faceCells.size(); i++)
+                    cross(s.T[p.faceCells[i]], sn_.T[itf.nbrCells[i]], m.C(p.faceCells[i]), sn_.mesh.C(itf.nbrCells[i]));
+            }
+        }
+        // physical patches: the face centre where max(cell value, patch value) >= iso.  Faces are enumerated per block side.
+        for (int pi = 0; pi < d.nPatches; pi++) {
+            const Patch& p = m.patches[pi];
+            size_t fi = 0;
+            for (int q = 0; q < d.patches[pi].nSides; q++) {
+                const int side = d.patches[pi].sides[q];
+                auto visit = [&](label i, label j, label k, Vec3 cf) {
+                    const label c = i + m.nx * (j + m.ny * k);
+                    const scalar Tb = p.type == B200_BC_ZERO_GRADIENT ? s.T[c] : p.Tb[fi];
+                    const scalar maxFace = std::max(s.T[c], Tb);
+                    for (size_t is = 0; is < nIso; is++) if (maxFace >= isoValues[is]) add(is, cf);
+                    fi++;
+                };
+                if (side == B200_XMIN || side == B200_XMAX) {
+                    const label i = side == B200_XMIN ? 0 : m.nx - 1;
+                    for (label k = 0; k < m.nz; k++) for (label j = 0; j < m.ny; j++) {
+                        Vec3 cf = m.C(i + m.nx * (j + m.ny * k)); cf.x = side == B200_XMIN ? m.px(0) : m.px(m.nx);
+                        visit(i, j, k, cf);
+                    }
+                } else if (side == B200_YMIN || side == B200_YMAX) {
+                    const label j = side == B200_YMIN ? 0 : m.ny - 1;
+                    for (label i = 0; i < m.nx; i++) for (label k = 0; k < m.nz; k++) {
+                        Vec3 cf = m.C(i + m.nx * (j + m.ny * k)); cf.y = side == B200_YMIN ? m.py(0) : m.py(m.ny);
+                        visit(i, j, k, cf);
+                    }
+                } else {
+                    const bool mine = side == B200_ZMIN ? (r == 0) : (r == R - 1);
+                    if (!mine) continue;
+                    const label k = side == B200_ZMIN ? 0 : m.nz - 1;
+                    for (label i = 0; i < m.nx; i++) for (label j = 0; j < m.ny; j++) {
+                        Vec3 cf = m.C(i + m.nx * (j + m.ny * k)); cf.z = side == B200_ZMIN ? m.pz(0) : m.pz(m.nz);
+                        visit(i, j, k, cf);
+                    }
+                }
+            }
+        }
+    }
+    dims.resize(nIso);
+    for (size_t i = 0; i < nIso; i++)
+        dims[i] = {std::max(bmax[i].x - bmin[i].x, 0.0), std::max(bmax[i].y - bmin[i].y, 0.0), std::max(bmax[i].z - bmin[i].z, 0.0)};
 }
 
 // One pass of the time loop body, SOLVER/additiveFoam.C:66-95

@@ -33,6 +33,7 @@ def load():
     L.afo_case_get_field.argtypes = [C.c_void_p, C.c_int, dp]
     L.afo_case_set_field.argtypes = [C.c_void_p, C.c_int, dp]
     L.afo_case_residual_log.argtypes = [C.c_void_p, dp, C.c_int32]
+    L.afo_case_melt_pool_dimensions.argtypes = [C.c_void_p, C.c_int32, dp, C.c_double, dp]
     L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
         getattr(L, f).restype = C.c_double
@@ -94,6 +95,12 @@ class OracleCase:
     def set_field(self, f, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         assert self.L.afo_case_set_field(self.h, f, P(a)) == 0
+
+    def melt_pool_dimensions(self, iso_values, angle_deg=0.0):
+        iso = np.ascontiguousarray(iso_values, dtype=np.float64)
+        out = np.empty(3 * len(iso))
+        self.L.afo_case_melt_pool_dimensions(self.h, len(iso), P(iso), angle_deg, P(out))
+        return out.reshape(-1, 3)
 
     def residual_log(self):
         out = np.empty(4096)

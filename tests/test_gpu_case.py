@@ -76,3 +76,30 @@ def test_rosenthal_conduction_only(ctx, oracle):
     case["controls"]["deltaT"] = 1e-6
     T, a, rg, ro = run_pair(ctx, oracle, case, 30, check_every=5)
     assert rg.nThermoCorr >= 2     # beam on => at least two passes (TEqn.H:58)
+
+
+# ---------------------------------------------------------------- meltPoolDimensions on the resident field
+@pytest.mark.parametrize("which", ["amb_explicit", "pbf_fixed_value"])
+def test_melt_pool_dimensions_parity(ctx, oracle, which):
+    """functionObjects/meltPoolDimensions/meltPoolDimensions.C:123-294 on the device-resident T against the oracle.  The
+    crossing points are computed with the same operations (no FMA contraction) and min/max do not depend on order, so on
+    identical T the spans agree to the last bit; on each side's own T after the same steps they inherit the 1e-9 of T."""
+    if which == "amb_explicit":
+        case, steps = cases.amb2018_02_b(n=(75, 13, 8)), 80
+    else:
+        case, steps = cases.multi_layer_pbf(n=(60, 24, 12), nHatch=2, endTime=0.002), 40
+        case["controls"]["deltaT"] = 1e-6
+    g = lib.Case(ctx, case)
+    o = ol.OracleCase(case, lib=oracle)
+    for _ in range(steps):
+        g.step(); o.step()
+    iso = [1620.0, 1410.0, 800.0, 1.0e5]
+    for angle in (0.0, 67.0):
+        dg, do = g.melt_pool_dimensions(iso, angle), o.melt_pool_dimensions(iso, angle)
+        assert do[0].min() > 0.0 and np.all(do[3] == 0.0)
+        assert np.max(np.abs(dg - do)) <= 1e-9 * np.max(do)
+    # identical field on both sides -> identical bits
+    T = o.field(abi.FIELD_T)
+    g.set_field(abi.FIELD_T, T)
+    assert np.array_equal(g.melt_pool_dimensions(iso, 67.0), o.melt_pool_dimensions(iso, 67.0))
+    g.close(); o.close()

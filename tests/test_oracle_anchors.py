@@ -333,3 +333,51 @@ def test_rosenthal_analytic(oracle):
         r = c.step()
     rosenthal.check(rosenthal.compare(c.field(abi.FIELD_T), r.time, case["mesh"]))
     c.close()
+
+
+# ---------------------------------------------------------------- meltPoolDimensions function object
+def test_melt_pool_dimensions_ellipsoid_and_rotation(oracle):
+    """meltPoolDimensions.C:123-294: an ellipsoidal Gaussian hot spot inside the block.  The isotherm is the ellipsoid
+    with semi-axes s_q*sqrt(ln(dT/(iso-T0))); linear interpolation between cell centres locates it to O(h^2).  Rotating
+    the frame by 90 degrees swaps the x and y spans."""
+    n = (64, 48, 40)
+    case = cases.amb2018_02_b(n=n)
+    m = case["mesh"]
+    h = [(m["max"][q] - m["min"][q]) / n[q] for q in range(3)]
+    o = ol.OracleCase(case, lib=oracle)
+    x, y, z = [m["min"][q] + (np.arange(n[q]) + 0.5) * h[q] for q in range(3)]
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    ctr = [m["min"][q] + 0.5 * (m["max"][q] - m["min"][q]) for q in range(3)]
+    s = [0.25 * (m["max"][0] - m["min"][0]), 0.2 * (m["max"][1] - m["min"][1]), 0.15 * (m["max"][2] - m["min"][2])]
+    T = 300.0 + 2000.0 * np.exp(-((X - ctr[0]) / s[0]) ** 2 - ((Y - ctr[1]) / s[1]) ** 2 - ((Z - ctr[2]) / s[2]) ** 2)
+    o.set_field(abi.FIELD_T, T.ravel())
+    iso = 1000.0
+    want = [2.0 * sq * np.sqrt(np.log(2000.0 / (iso - 300.0))) for sq in s]
+    d0 = o.melt_pool_dimensions([iso, 5000.0], 0.0)
+    for q in range(3):
+        assert d0[0, q] == pytest.approx(want[q], abs=0.6 * h[q])
+    assert np.all(d0[1] == 0.0)                                  # an isovalue nothing reaches: max(span, 0) = 0
+    d90 = o.melt_pool_dimensions([iso], 90.0)
+    assert d90[0, 0] == pytest.approx(d0[0, 1], rel=1e-12) and d90[0, 1] == pytest.approx(d0[0, 0], rel=1e-12)
+    assert d90[0, 2] == d0[0, 2]
+    o.close()
+
+
+def test_melt_pool_dimensions_boundary_faces(oracle):
+    """Physical boundary faces contribute their face centre when the cell (or patch) value reaches the isovalue
+    (meltPoolDimensions.C:226-262): for T linear in x every boundary cell beyond the crossing plane counts, so the box runs
+    from the crossing plane to xmax and over the whole y and z extent of the block."""
+    n = (40, 10, 8)
+    case = cases.amb2018_02_b(n=n)
+    m = case["mesh"]
+    o = ol.OracleCase(case, lib=oracle)
+    hx = (m["max"][0] - m["min"][0]) / n[0]
+    x = m["min"][0] + (np.arange(n[0]) + 0.5) * hx
+    T = np.broadcast_to(300.0 + 1.0e6 * (x - m["min"][0]), (n[2], n[1], n[0])).copy()
+    o.set_field(abi.FIELD_T, T.ravel())
+    xstar = m["min"][0] + 0.3712 * (m["max"][0] - m["min"][0])
+    iso = 300.0 + 1.0e6 * (xstar - m["min"][0])
+    d = o.melt_pool_dimensions([iso], 0.0)[0]
+    assert d[0] == pytest.approx(m["min"][0] + (m["max"][0] - m["min"][0]) - xstar, rel=1e-9)
+    assert d[1] == pytest.approx((m["max"][1] - m["min"][1]), rel=1e-12) and d[2] == pytest.approx((m["max"][2] - m["min"][2]), rel=1e-12)
+    o.close()

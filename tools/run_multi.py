@@ -31,6 +31,8 @@ assert g.n_local == partition.local_cells(n, rank, world)
 reps = [g.step() for _ in range(steps)]
 T = partition.gather_field(g.field(abi.FIELD_T), n, rank, world, dist, device="cuda")
 A = partition.gather_field(g.field(abi.FIELD_ALPHA_SOLID), n, rank, world, dist, device="cuda")
+ISO = [1620.0, 1410.0, 600.0]
+mp = g.melt_pool_dimensions(ISO, 30.0)     # collective
 ok = True
 if rank == 0:
     import oracle_lib as ol
@@ -41,8 +43,10 @@ if rank == 0:
     eA = float(np.max(np.abs(A - Ao)))
     its = max(abs(a.lastSolveIterations - b.lastSolveIterations) for a, b in zip(reps, oreps))
     dts = max(abs(a.deltaT - b.deltaT) / b.deltaT for a, b in zip(reps, oreps))
-    ok = eT < 1e-9 and eA < 1e-9 and its <= 1 and dts < 1e-10
-    print(f"MULTI {mode} ranks={world} relLinf(T)={eT:.3e} Linf(alpha)={eA:.3e} iterdiff={its} dtdiff={dts:.2e} Tmax={To.max():.1f} "
+    mpo = o.melt_pool_dimensions(ISO, 30.0)
+    eM = float(np.max(np.abs(mp - mpo)) / max(np.max(np.abs(mpo)), 1e-300))
+    ok = eT < 1e-9 and eA < 1e-9 and its <= 1 and dts < 1e-10 and eM < 1e-9 and mpo[2].max() > 0
+    print(f"MULTI {mode} ranks={world} relLinf(T)={eT:.3e} Linf(alpha)={eA:.3e} iterdiff={its} dtdiff={dts:.2e} meltPool={eM:.2e} Tmax={To.max():.1f} "
           f"{'OK' if ok else 'FAIL'}", flush=True)
 g.close(); ctx.close()
 dist.barrier()
