@@ -308,6 +308,20 @@ int b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* iso
     c->p->meltPoolDimensions(nIso, isoValues, scanPathAngleDeg, dims);
     B200_CATCH
 }
+int b200_case_solidification_enable(b200_case* c, const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents)
+{
+    B200_TRY
+    B200_CHECK(c && boxMin && boxMax, "solidification_enable: bad arguments");
+    c->p->solidificationEnable(boxMin, boxMax, isoValue, maxEvents);
+    B200_CATCH
+}
+int b200_case_solidification_events(b200_case* c, double* events, int64_t maxEvents, int64_t* nRecorded)
+{
+    B200_TRY
+    B200_CHECK(c && nRecorded, "solidification_events: bad arguments");
+    *nRecorded = c->p->solidificationEvents(events, maxEvents);
+    B200_CATCH
+}
 int b200_case_kernel_launches(b200_case*, int64_t* launches)
 {
     *launches = g_launches;

@@ -28,7 +28,7 @@ Ctx::Ctx(int dev, const void* uniqueId, int rank_, int nranks_) : device(dev), r
 const char* prof_name(int cat)
 {
     static const char* names[PC_NCAT] = {"amul", "sweep_fwd", "sweep_bwd", "factor", "vector", "normfactor", "ctrl", "props", "dinum",
-                                         "faces", "assemble", "corrector", "alpha", "boundary", "qdot", "copy", "comm"};
+                                         "faces", "assemble", "corrector", "alpha", "boundary", "qdot", "copy", "comm", "funcobj"};
     return cat >= 0 && cat < PC_NCAT ? names[cat] : "?";
 }
 

@@ -16,7 +16,7 @@ namespace b200 {
 
 // kernel groups timed by the built-in CUDA-event profiler (bench.py's roofline numbers)
 enum ProfCat { PC_AMUL = 0, PC_SWEEP_FWD, PC_SWEEP_BWD, PC_FACTOR, PC_VECTOR, PC_NORMFACTOR, PC_CTRL, PC_PROPS, PC_DINUM, PC_FACES,
-               PC_ASSEMBLE, PC_CORRECTOR, PC_ALPHA, PC_BOUNDARY, PC_QDOT, PC_COPY, PC_COMM, PC_NCAT };
+               PC_ASSEMBLE, PC_CORRECTOR, PC_ALPHA, PC_BOUNDARY, PC_QDOT, PC_COPY, PC_COMM, PC_FUNCOBJ, PC_NCAT };
 const char* prof_name(int cat);
 
 // Peer-memory mailbox of the small all-reduces (Krylov dot products, residual norms, time-step numbers): every rank stores

@@ -157,6 +157,7 @@ ThermalCase::~ThermalCase()
     dev_free(upper); dev_free(wbuf); dev_free(d_thermo);
     dev_free(red.partials); dev_free(red.ticket); dev_free(red.result);
     if (h_red) cudaFreeHost(h_red);
+    dev_free(solidEv); dev_free(solidKeys); dev_free(solidCount);
     for (auto& si : sides) { dev_free(si.valueFraction); dev_free(si.Tb); dev_free(si.intCoeff); dev_free(si.bouCoeff); }
 }
 
@@ -194,6 +195,71 @@ void ThermalCase::setField(int fIn, const double* in)
     }
     if (f == B200_FIELD_ALPHA_SOLID) B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     ctx->sync();
+}
+
+// solidificationData.C:99-131 setOverlapCells: a cell belongs when its bounding box grown by 1e-10 overlaps the box (inclusive
+// comparisons); on the block mesh that is an index box, found per axis with the same expressions.
+void ThermalCase::solidificationEnable(const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents)
+{
+    B200_CHECK(!solidOn, "solidificationData is already enabled on this case");
+    B200_CHECK(maxEvents > 0, "solidificationData: maxEvents must be positive");
+    const double ext = 1e-10;
+    auto range = [&](int n, double o, double h, int k0, double lo, double hi, int& a, int& b) {
+        a = n; b = 0;
+        for (int i = 0; i < n; i++) {
+            const bool in = (o + (i + k0) * h) - ext <= hi && (o + (i + 1 + k0) * h) + ext >= lo;
+            if (in) { a = std::min(a, i); b = std::max(b, i + 1); }
+        }
+        if (a > b) { a = 0; b = 0; }
+    };
+    range(dims.nx, geo.ox, geo.dx, 0, boxMin[0], boxMax[0], solidBox.i0, solidBox.i1);
+    range(dims.ny, geo.oy, geo.dy, 0, boxMin[1], boxMax[1], solidBox.j0, solidBox.j1);
+    range(dims.nz, geo.oz, geo.dz, geo.k0, boxMin[2], boxMax[2], solidBox.k0, solidBox.k1);
+    solidIso = isoValue; solidMax = maxEvents; solidExec = 0;
+    solidR = allocField();                               // zero: fvc::ddt(T) before the first step (:67-78)
+    solidEv = dev_alloc<double>((size_t)maxEvents * 7);
+    solidKeys = dev_alloc<long long>((size_t)maxEvents);
+    solidCount = dev_alloc<unsigned long long>(1);
+    B200_CUDA(cudaMemsetAsync(solidCount, 0, sizeof(unsigned long long), ctx->stream));
+    solidOn = true;
+}
+
+void ThermalCase::solidificationExecute()
+{
+    const int64_t nBox = (int64_t)std::max(solidBox.i1 - solidBox.i0, 0) * std::max(solidBox.j1 - solidBox.j0, 0) *
+                         std::max(solidBox.k1 - solidBox.k0, 0);
+    solidExec++;
+    haloExchange(T);                                     // collective: every rank calls it, with or without overlap cells
+    if (nBox == 0) return;
+    ProfScope ps_(ctx, PC_FUNCOBJ);
+    SolidArgs a;
+    a.box = solidBox; a.iso = solidIso; a.time = time_; a.rDeltaT = 1.0 / deltaT_; a.T = T; a.Told = Told; a.R = solidR;
+    a.events = solidEv; a.keys = solidKeys; a.count = solidCount; a.maxEvents = solidMax; a.execIndex = solidExec;
+    k_solidification<<<flat_grid(ctx, nBox), BLK, 0, ctx->stream>>>(dims, geo, sidesDev, a);
+    B200_LAUNCH_CHECK();
+}
+
+// Events in the reference's order (time step, then cell).  Returns the number recorded; entries beyond the capacity given
+// to solidificationEnable were dropped, which the caller sees as a return value above that capacity.
+int64_t ThermalCase::solidificationEvents(double* out, int64_t maxOut)
+{
+    B200_CHECK(solidOn, "solidificationData is not enabled on this case");
+    unsigned long long cnt = 0;
+    d2h(&cnt, solidCount, 1, ctx->stream);
+    ctx->sync();
+    const int64_t have = std::min<int64_t>((int64_t)cnt, solidMax);
+    if (out && have > 0 && maxOut > 0) {
+        std::vector<double> ev((size_t)have * 7);
+        std::vector<long long> keys((size_t)have);
+        d2h(ev.data(), solidEv, (size_t)have * 7, ctx->stream);
+        d2h(keys.data(), solidKeys, (size_t)have, ctx->stream);
+        ctx->sync();
+        std::vector<int64_t> order((size_t)have);
+        for (int64_t i = 0; i < have; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return keys[x] < keys[y]; });
+        for (int64_t i = 0; i < std::min(have, maxOut); i++) std::memcpy(out + 7 * i, ev.data() + 7 * order[i], 7 * sizeof(double));
+    }
+    return (int64_t)cnt;
 }
 
 // functionObjects/meltPoolDimensions: dims[3*i..] = max(span, 0) of isotherm i in the scan-path frame; the field never leaves HBM
@@ -475,6 +541,7 @@ void ThermalCase::step(b200_step_report* rep)
         rep->nSolveIterations = iterSum; rep->lastSolveIterations = perf.nIterations;
         rep->lastInitialResidual = perf.initialResidual; rep->lastFinalResidual = perf.finalResidual;
     }
+    if (solidOn) solidificationExecute();                              // [UPSTREAM] Time::run -> functionObjectList::execute
 }
 
 // heatSourceModel::qDot() on its own (B2 of the drop-in boundary)

@@ -57,6 +57,8 @@ public:
     void getField(int field, double* out);
     void setField(int field, const double* in);
     void meltPoolDimensions(int nIso, const double* isoValues, double scanPathAngleDeg, double* dims);
+    void solidificationEnable(const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents);
+    int64_t solidificationEvents(double* out, int64_t maxOut);          // returns the number recorded so far (may exceed capacity)
 
     Ctx* ctx;
 private:
@@ -88,6 +90,16 @@ private:
     RedWork red{};
     double* h_red = nullptr;             // pinned mirror of red.result
     const double* bouPtrs[2] = {nullptr, nullptr};
+
+    // functionObjects/solidificationData state
+    bool solidOn = false;
+    BoxRange solidBox{};
+    double solidIso = 0;
+    double *solidR = nullptr, *solidEv = nullptr;
+    long long* solidKeys = nullptr;
+    unsigned long long* solidCount = nullptr;
+    int64_t solidMax = 0, solidExec = 0;
+    void solidificationExecute();
 
     double* field(int f);
     double* allocField();

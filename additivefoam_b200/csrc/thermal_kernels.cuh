@@ -437,4 +437,60 @@ __global__ void __launch_bounds__(BLK) k_melt_pool(BlockDims d, Geom g, SidesDev
     grid_reduce<6>(v, ops, red, R_MPOOL, smem);
 }
 
+// functionObjects/solidificationData/solidificationData.C:140-187 over the index box of the overlap cells.  A cell that was above
+// the isovalue at the old time and is at or below it now appends {x, y, z, t, |R|, max(G, small), |R|/G}: G = mag(fvc::grad(T))
+// ("Gauss linear": sum of Sf*T_f over the six faces / V, patch value on physical boundary faces, w*own + (1-w)*nbr on processor
+// faces), R the cooling rate kept from the previous execute.  R is then refreshed to (T - Told)/deltaT -- only where T is above
+// the isovalue, the only cells whose R a later event can read.  Events land in arrival order; key = (execute index, cell)
+// lets the reader restore the reference's append order.
+struct SolidArgs {
+    BoxRange box;
+    double iso, time, rDeltaT;
+    const double *T, *Told;
+    double* R;
+    double* events;                 // maxEvents x 7
+    long long* keys;                // maxEvents
+    unsigned long long* count;
+    long long maxEvents, execIndex;
+};
+
+__global__ void __launch_bounds__(BLK) k_solidification(BlockDims d, Geom g, SidesDev sd, SolidArgs a)
+{
+    const int bx = a.box.i1 - a.box.i0, by = a.box.j1 - a.box.j0, bz = a.box.k1 - a.box.k0;
+    const int nx = d.nx; const int64_t nxny = (int64_t)d.nx * d.ny;
+    const int64_t total = (int64_t)bx * by * bz;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int i = a.box.i0 + (int)(q % bx);
+        const int64_t rowq = q / bx;
+        const int j = a.box.j0 + (int)(rowq % by), k = a.box.k0 + (int)(rowq / by);
+        const int64_t c = i + (int64_t)nx * j + nxny * k;
+        const double Tc = a.T[c], Tc0 = a.Told[c];
+        if (Tc0 > a.iso && Tc <= a.iso) {
+            auto faceValue = [&](int s) -> double {
+                const int type = sd.type[s];
+                if (type == SIDE_PROCESSOR) { const double Tn = a.T[s == B200_ZMIN ? c - nxny : c + nxny]; return 0.5 * Tc + (1.0 - 0.5) * Tn; }
+                if (type == B200_BC_ZERO_GRADIENT) return Tc;
+                return sd.Tb[s][side_index(d, s, i, j, k)];
+            };
+            const double Tw = i > 0 ? 0.5 * (a.T[c - 1] - Tc) + Tc : faceValue(B200_XMIN);
+            const double Te = i < nx - 1 ? 0.5 * (Tc - a.T[c + 1]) + a.T[c + 1] : faceValue(B200_XMAX);
+            const double Ts = j > 0 ? 0.5 * (a.T[c - nx] - Tc) + Tc : faceValue(B200_YMIN);
+            const double Tn = j < d.ny - 1 ? 0.5 * (Tc - a.T[c + nx]) + a.T[c + nx] : faceValue(B200_YMAX);
+            const double Tb = k > 0 ? 0.5 * (a.T[c - nxny] - Tc) + Tc : faceValue(B200_ZMIN);
+            const double Tt = k < d.nz - 1 ? 0.5 * (Tc - a.T[c + nxny]) + a.T[c + nxny] : faceValue(B200_ZMAX);
+            const double gx = (g.sfx * Te - g.sfx * Tw) / g.V, gy = (g.sfy * Tn - g.sfy * Ts) / g.V, gz = (g.sfz * Tt - g.sfz * Tb) / g.V;
+            const double G = sqrt(gx * gx + gy * gy + gz * gz);
+            const double Ri = fabs(a.R[c]), Gi = fmax(G, 1e-15);
+            const unsigned long long slot = atomicAdd(a.count, 1ull);
+            if ((long long)slot < a.maxEvents) {
+                double* e = a.events + 7 * slot;
+                e[0] = g.ox + (i + 0.5) * g.dx; e[1] = g.oy + (j + 0.5) * g.dy; e[2] = g.oz + (k + g.k0 + 0.5) * g.dz;
+                e[3] = a.time; e[4] = Ri; e[5] = Gi; e[6] = Ri / Gi;
+                a.keys[slot] = (a.execIndex << 40) | (long long)c;
+            }
+        }
+        if (Tc > a.iso) a.R[c] = a.rDeltaT * (Tc - Tc0);
+    }
+}
+
 } // namespace b200

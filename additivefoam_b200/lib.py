@@ -28,7 +28,8 @@ SYMBOLS = [
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
-    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_kernel_launches",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_solidification_enable",
+    "b200_case_solidification_events", "b200_case_kernel_launches",
     "b200_scan_path_parse",
 ]
 
@@ -102,6 +103,8 @@ def load():
     L.b200_case_get_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_set_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_melt_pool_dimensions.argtypes = [vp, C.c_int32, dp, C.c_double, dp]
+    L.b200_case_solidification_enable.argtypes = [vp, dp, dp, C.c_double, C.c_int64]
+    L.b200_case_solidification_events.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.b200_case_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.b200_scan_path_parse.argtypes = [C.c_char_p, dp, C.c_int32]
     _lib = L
@@ -302,6 +305,22 @@ class Case:
         out = np.empty(3 * len(iso))
         _check(self.L.b200_case_melt_pool_dimensions(self.h, len(iso), _P(iso), float(angle_deg), _P(out)))
         return out.reshape(-1, 3)
+
+    def solidification_enable(self, box_min, box_max, iso_value, max_events=1 << 20):
+        """solidificationData function object (solidificationData.C): record cooling events on the device from the next step on."""
+        lo, hi = np.asarray(box_min, dtype=np.float64), np.asarray(box_max, dtype=np.float64)
+        self._solid_cap = int(max_events)
+        _check(self.L.b200_case_solidification_enable(self.h, _P(lo), _P(hi), float(iso_value), self._solid_cap))
+
+    def solidification_events(self):
+        """(n, 7) rows x,y,z,ts,cr,g,v of this rank in the reference's order; raises if the device buffer overflowed."""
+        n = C.c_int64()
+        _check(self.L.b200_case_solidification_events(self.h, None, 0, C.byref(n)))
+        if n.value > self._solid_cap:
+            raise RuntimeError(f"solidificationData: {n.value} events exceed the capacity {self._solid_cap} given at enable")
+        out = np.empty((max(n.value, 1), 7))
+        _check(self.L.b200_case_solidification_events(self.h, _P(out), n.value, C.byref(n)))
+        return out[:n.value]
 
     def close(self):
         if self.h:

@@ -250,6 +250,15 @@ int  b200_case_set_field(b200_case* c, int32_t field, const double* in);
  * reaches it; dims[3*i+0..2] = max(span, 0) in x, y, z -- the three numbers the reference logs per isoValue (:283-291).
  * Collective over the ranks of the context. */
 int  b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* isoValues, double scanPathAngleDeg, double* dims);
+/* functionObjects/solidificationData/solidificationData.C: once enabled, every b200_case_step ends with the function object's
+ * execute() (:140-187) on the device: each cell of the box (setOverlapCells, :99-131) that cooled through isoValue during the
+ * step appends {x, y, z, t, |R|, max(G, small), |R|/G} to a device buffer of maxEvents rows; G = mag(fvc::grad(T)) ("Gauss
+ * linear"), R the cooling rate kept from the previous execute, as in the reference.  Per rank, like the reference's
+ * data_<proc>.csv (:189-222). */
+int  b200_case_solidification_enable(b200_case* c, const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents);
+/* Copies this rank's events, in the reference's append order (time step, then cell), into events[maxEvents][7] (may be NULL to
+ * query).  *nRecorded = events seen so far; a value above the capacity given at enable means the excess was dropped. */
+int  b200_case_solidification_events(b200_case* c, double* events, int64_t maxEvents, int64_t* nRecorded);
 /* Device time (ms) spent in the kernels of the last step by group, for the benchmark:
  * [0] properties+dt numbers, [1] heat source, [2] assembly, [3] corrector fold+alpha update,
  * [4] Krylov solve. */

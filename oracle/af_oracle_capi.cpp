@@ -262,6 +262,23 @@ int afo_case_melt_pool_dimensions(void* h, label nIso, const scalar* iso, scalar
     for (label i = 0; i < nIso; i++) { dims[3 * i] = out[i].x; dims[3 * i + 1] = out[i].y; dims[3 * i + 2] = out[i].z; }
     return 0;
 }
+int afo_case_solidification_enable(void* h, const scalar boxMin[3], const scalar boxMax[3], scalar isoValue)
+{
+    ((Case*)h)->solidificationEnable({boxMin[0], boxMin[1], boxMin[2]}, {boxMax[0], boxMax[1], boxMax[2]}, isoValue);
+    return 0;
+}
+// events of all emulated ranks, rank by rank in append order (the order of the reference's data_<proc>.csv files)
+int64_t afo_case_solidification_events(void* h, scalar* out, int64_t maxEvents)
+{
+    Case* c = (Case*)h;
+    int64_t n = 0;
+    for (auto& ev : c->solidEvents)
+        for (auto& e : ev) {
+            if (out && n < maxEvents) std::memcpy(out + 7 * n, e.data(), sizeof(scalar) * 7);
+            n++;
+        }
+    return n;
+}
 scalar afo_case_time(void* h) { return ((Case*)h)->time; }
 scalar afo_case_Tliq(void* h) { return ((Case*)h)->Tliq; }
 scalar afo_case_Tsol(void* h) { return ((Case*)h)->Tsol; }

@@ -210,6 +210,15 @@ struct Case {
     void thermoSource(int r);
     SolverPerf solveCorrector(bool explicitSolve, scalar rDeltaT, scalar rDeltaTEuler);
     void meltPoolDimensions(const std::vector<scalar>& isoValues, scalar scanPathAngleDeg, std::vector<Vec3>& dims);
+    // functionObjects/solidificationData
+    bool solidOn = false;
+    Vec3 solidBoxMin{0, 0, 0}, solidBoxMax{0, 0, 0};
+    scalar solidIso = 0;
+    std::vector<Field> solidR;                          // R_ per rank
+    std::vector<std::vector<label>> solidCells;         // overlapCells per rank
+    std::vector<std::vector<std::array<scalar, 7>>> solidEvents;   // per rank, in append order
+    void solidificationEnable(Vec3 boxMin, Vec3 boxMax, scalar isoValue);
+    void solidificationExecute();
 };
 
 // ---------------------------------------------------------------------------------------
@@ -751,6 +760,87 @@ inline void Case::meltPoolDimensions(const std::vector<scalar>& isoValues, scala
         dims[i] = {std::max(bmax[i].x - bmin[i].x, 0.0), std::max(bmax[i].y - bmin[i].y, 0.0), std::max(bmax[i].z - bmin[i].z, 0.0)};
 }
 
+// SOLVER/functionObjects/solidificationData/solidificationData.C:55-83 (constructor: R_ = fvc::ddt(T) = 0 before the first step)
+// and :99-131 (setOverlapCells: cells whose bounding box, grown by 1e-10, overlaps the box; inclusive comparisons as
+// [UPSTREAM] boundBox::overlaps)
+inline void Case::solidificationEnable(Vec3 boxMin, Vec3 boxMax, scalar isoValue)
+{
+    solidOn = true; solidBoxMin = boxMin; solidBoxMax = boxMax; solidIso = isoValue;
+    solidR.assign(R, Field()); solidCells.assign(R, {}); solidEvents.assign(R, {});
+    const scalar ext = 1e-10;
+    for (int r = 0; r < R; r++) {
+        const Mesh& m = rk[r].mesh;
+        solidR[r].assign(m.nCells(), 0.0);
+        for (label c = 0; c < m.nCells(); c++) {
+            const label i = c % m.nx, j = (c / m.nx) % m.ny, k = c / (m.nx * m.ny);
+            const Vec3 lo{m.px(i) - ext, m.py(j) - ext, m.pz(k) - ext}, hi{m.px(i + 1) + ext, m.py(j + 1) + ext, m.pz(k + 1) + ext};
+            if (lo.x <= boxMax.x && hi.x >= boxMin.x && lo.y <= boxMax.y && hi.y >= boxMin.y && lo.z <= boxMax.z && hi.z >= boxMin.z)
+                solidCells[r].push_back(c);
+        }
+    }
+}
+
+// solidificationData.C:140-187, run after each completed time step ([UPSTREAM] Time::run -> functionObjectList::execute):
+// G = mag(fvc::grad(T)) with "Gauss linear" ([UPSTREAM] gaussGrad: sum of Sf*T_f over the faces / V; linear T_f between
+// cells, patch value on boundary faces, the coupled average on processor faces); a cell that was above the isovalue at the
+// old time and is at or below it now is recorded with the cooling rate R_ kept from the PREVIOUS execute; only then is R_
+// refreshed to fvc::ddt(T) = (T - T.oldTime())/deltaT (Euler).
+inline void Case::solidificationExecute()
+{
+    const scalar rDeltaT = 1.0 / deltaT;
+    for (int r = 0; r < R; r++) {
+        RankState& s = rk[r];
+        const Mesh& m = s.mesh;
+        const label nx = m.nx, ny = m.ny, nz = m.nz, nxny = nx * ny;
+        // boundary value lookup: physical patch faces by side, processor neighbours by plane
+        std::vector<const scalar*> sideTb(6, nullptr);
+        for (int pi = 0; pi < d.nPatches; pi++) {
+            size_t off = 0;
+            for (int q = 0; q < d.patches[pi].nSides; q++) {
+                const int side = d.patches[pi].sides[q];
+                size_t cnt;
+                if (side <= B200_XMAX) cnt = (size_t)ny * nz;
+                else if (side <= B200_YMAX) cnt = (size_t)nx * nz;
+                else { const bool mine = side == B200_ZMIN ? (r == 0) : (r == R - 1); cnt = mine ? (size_t)nx * ny : 0; }
+                if (cnt) sideTb[side] = m.patches[pi].Tb.data() + off;
+                off += cnt;
+            }
+        }
+        auto faceValue = [&](int side, label i, label j, label k, scalar Tc) -> scalar {
+            if (side >= B200_ZMIN) {
+                const int nb = side == B200_ZMIN ? r - 1 : r + 1;
+                if (nb >= 0 && nb < R) {                         // coupled face ([UPSTREAM] surfaceInterpolationScheme::interpolate): w*own + (1-w)*nbr
+                    const RankState& o = rk[nb];
+                    const scalar Tn = o.T[i + nx * (j + ny * (side == B200_ZMIN ? o.mesh.nz - 1 : 0))];
+                    return 0.5 * Tc + (1.0 - 0.5) * Tn;
+                }
+            }
+            if (!sideTb[side]) return Tc;                        // side not listed in any patch (treated as zeroGradient)
+            const size_t fi = side <= B200_XMAX ? (size_t)j + (size_t)ny * k : side <= B200_YMAX ? (size_t)k + (size_t)nz * i : (size_t)j + (size_t)ny * i;
+            return sideTb[side][fi];
+        };
+        for (label c : solidCells[r]) {
+            if (s.Told[c] > solidIso && s.T[c] <= solidIso) {
+                const label i = c % nx, j = (c / nx) % ny, k = c / nxny;
+                const scalar Tc = s.T[c];
+                const scalar sfx = m.dy * m.dz, sfy = m.dx * m.dz, sfz = m.dx * m.dy;
+                const scalar Tw = i > 0 ? 0.5 * (s.T[c - 1] - Tc) + Tc : faceValue(B200_XMIN, i, j, k, Tc);
+                const scalar Te = i < nx - 1 ? 0.5 * (Tc - s.T[c + 1]) + s.T[c + 1] : faceValue(B200_XMAX, i, j, k, Tc);
+                const scalar Ts = j > 0 ? 0.5 * (s.T[c - nx] - Tc) + Tc : faceValue(B200_YMIN, i, j, k, Tc);
+                const scalar Tn = j < ny - 1 ? 0.5 * (Tc - s.T[c + nx]) + s.T[c + nx] : faceValue(B200_YMAX, i, j, k, Tc);
+                const scalar Tb = k > 0 ? 0.5 * (s.T[c - nxny] - Tc) + Tc : faceValue(B200_ZMIN, i, j, k, Tc);
+                const scalar Tt = k < nz - 1 ? 0.5 * (Tc - s.T[c + nxny]) + s.T[c + nxny] : faceValue(B200_ZMAX, i, j, k, Tc);
+                const scalar gx = (sfx * Te - sfx * Tw) / m.V, gy = (sfy * Tn - sfy * Ts) / m.V, gz = (sfz * Tt - sfz * Tb) / m.V;
+                const scalar G = std::sqrt(gx * gx + gy * gy + gz * gz);
+                const scalar Ri = std::fabs(solidR[r][c]), Gi = std::max(G, small_);
+                const Vec3 pt = m.C(c);
+                solidEvents[r].push_back({pt.x, pt.y, pt.z, time, Ri, Gi, Ri / Gi});
+            }
+        }
+        for (label c = 0; c < m.nCells(); c++) solidR[r][c] = rDeltaT * (s.T[c] - s.Told[c]);
+    }
+}
+
 // One pass of the time loop body, SOLVER/additiveFoam.C:66-95
 inline void Case::step(b200_step_report* rep)
 {
@@ -816,6 +906,7 @@ inline void Case::step(b200_step_report* rep)
         rep->thermoResidual = residual; rep->nSolveIterations = iterSum; rep->lastSolveIterations = perf.nIterations;
         rep->lastInitialResidual = perf.initialResidual; rep->lastFinalResidual = perf.finalResidual;
     }
+    if (solidOn) solidificationExecute();
 }
 
 } // namespace afo

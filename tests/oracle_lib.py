@@ -34,6 +34,9 @@ def load():
     L.afo_case_set_field.argtypes = [C.c_void_p, C.c_int, dp]
     L.afo_case_residual_log.argtypes = [C.c_void_p, dp, C.c_int32]
     L.afo_case_melt_pool_dimensions.argtypes = [C.c_void_p, C.c_int32, dp, C.c_double, dp]
+    L.afo_case_solidification_enable.argtypes = [C.c_void_p, dp, dp, C.c_double]
+    L.afo_case_solidification_events.argtypes = [C.c_void_p, dp, C.c_int64]
+    L.afo_case_solidification_events.restype = C.c_int64
     L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
         getattr(L, f).restype = C.c_double
@@ -101,6 +104,16 @@ class OracleCase:
         out = np.empty(3 * len(iso))
         self.L.afo_case_melt_pool_dimensions(self.h, len(iso), P(iso), angle_deg, P(out))
         return out.reshape(-1, 3)
+
+    def solidification_enable(self, box_min, box_max, iso_value):
+        lo, hi = np.asarray(box_min, dtype=np.float64), np.asarray(box_max, dtype=np.float64)
+        self.L.afo_case_solidification_enable(self.h, P(lo), P(hi), iso_value)
+
+    def solidification_events(self):
+        n = self.L.afo_case_solidification_events(self.h, None, 0)
+        out = np.empty((max(n, 1), 7))
+        self.L.afo_case_solidification_events(self.h, P(out), n)
+        return out[:n]
 
     def residual_log(self):
         out = np.empty(4096)

@@ -103,3 +103,45 @@ def test_melt_pool_dimensions_parity(ctx, oracle, which):
     g.set_field(abi.FIELD_T, T)
     assert np.array_equal(g.melt_pool_dimensions(iso, 67.0), o.melt_pool_dimensions(iso, 67.0))
     g.close(); o.close()
+
+
+# ---------------------------------------------------------------- solidificationData on the device
+@pytest.mark.parametrize("which", ["amb_explicit", "amb_implicit_box", "pbf_fixed_value"])
+def test_solidification_events_parity(ctx, oracle, which):
+    """functionObjects/solidificationData/solidificationData.C:140-187 executed on the device at the end of every step against
+    the oracle: same events in the same order; positions bit-equal, times/rates/gradients to the accuracy T carries."""
+    box = ([-1, -1, -1], [1, 1, 1])
+    if which == "amb_explicit":
+        case, steps = cases.amb2018_02_b(n=(75, 13, 16)), 200
+    elif which == "amb_implicit_box":
+        case, steps = cases.amb2018_02_b(n=(60, 12, 16), explicitSolve=0, maxDi=10.0), 90
+        box = ([0.0002, -0.00005, -1], [0.0009, 1, 1])
+    else:
+        case, steps = cases.multi_layer_pbf(n=(60, 24, 12), nHatch=2, endTime=0.002), 220
+        case["controls"]["deltaT"] = 1e-6
+    g = lib.Case(ctx, case)
+    o = ol.OracleCase(case, lib=oracle)
+    g.solidification_enable(box[0], box[1], 1620.0)
+    o.solidification_enable(box[0], box[1], 1620.0)
+    for _ in range(steps):
+        g.step(); o.step()
+    eg, eo = g.solidification_events(), o.solidification_events()
+    assert len(eo) > 10 and eg.shape == eo.shape
+    assert np.array_equal(eg[:, :3], eo[:, :3])
+    assert np.allclose(eg[:, 3], eo[:, 3], rtol=1e-11, atol=0)
+    assert np.allclose(eg[:, 4:], eo[:, 4:], rtol=1e-6)
+    assert helpers.rel_linf(g.field(abi.FIELD_T), o.field(abi.FIELD_T)) < TOL      # the hook does not disturb the step
+    g.close(); o.close()
+
+
+def test_solidification_overflow_is_reported(ctx):
+    case = cases.amb2018_02_b(n=(75, 13, 16))
+    g = lib.Case(ctx, case)
+    g.solidification_enable([-1, -1, -1], [1, 1, 1], 1620.0, max_events=4)
+    for _ in range(200):
+        g.step()
+    with pytest.raises(RuntimeError, match="exceed the capacity"):
+        g.solidification_events()
+    with pytest.raises(RuntimeError, match="already enabled"):
+        g.solidification_enable([-1, -1, -1], [1, 1, 1], 1620.0)
+    g.close()

@@ -23,3 +23,13 @@ def test_two_rank_parity(mode):
            "--master-port", "29533", os.path.join(ROOT, "tools", "run_multi.py"), mode, "30"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_two_rank_function_objects():
+    """meltPoolDimensions and solidificationData across the slab interface (processor faces on every cell)."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "tools", "run_multi.py"), "funcobj", "120"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -381,3 +381,66 @@ def test_melt_pool_dimensions_boundary_faces(oracle):
     assert d[0] == pytest.approx(m["min"][0] + (m["max"][0] - m["min"][0]) - xstar, rel=1e-9)
     assert d[1] == pytest.approx((m["max"][1] - m["min"][1]), rel=1e-12) and d[2] == pytest.approx((m["max"][2] - m["min"][2]), rel=1e-12)
     o.close()
+
+
+# ---------------------------------------------------------------- solidificationData function object
+def test_solidification_events_against_numpy(oracle):
+    """solidificationData.C:140-187 re-derived from field snapshots in numpy: a cell is recorded in the step where it cools
+    through the isovalue; G is the Gauss-linear gradient (central differences inside the block), and the cooling rate is the
+    one stored by the PREVIOUS execute, (T^{n-1} - T^{n-2})/dt^{n-1} -- not the current step's."""
+    n = (75, 13, 20)
+    case = cases.amb2018_02_b(n=n)
+    m = case["mesh"]
+    h = [(m["max"][q] - m["min"][q]) / n[q] for q in range(3)]
+    o = ol.OracleCase(case, lib=oracle)
+    iso = 1620.0
+    o.solidification_enable([-1, -1, -1], [1, 1, 1], iso)
+    shape = (n[2], n[1], n[0])
+    snaps = [o.field(abi.FIELD_T).reshape(shape).copy()]
+    want = []
+    Rprev = np.zeros(shape)
+    for step in range(260):
+        rep = o.step()
+        T = o.field(abi.FIELD_T).reshape(shape).copy()
+        T0 = snaps[-1]
+        ev = np.argwhere((T0 > iso) & (T <= iso))                    # C order = cell order (k, j, i)
+        for k, j, i in ev:
+            if not (0 < i < n[0] - 1 and 0 < j < n[1] - 1 and 0 < k < n[2] - 1):
+                continue                                              # boundary cells are compared on the GPU side only
+            g = np.array([(T[k, j, i + 1] - T[k, j, i - 1]) / (2 * h[0]), (T[k, j + 1, i] - T[k, j - 1, i]) / (2 * h[1]),
+                          (T[k + 1, j, i] - T[k - 1, j, i]) / (2 * h[2])])
+            G = max(np.linalg.norm(g), 1e-15)
+            R = abs(Rprev[k, j, i])
+            want.append([m["min"][0] + (i + 0.5) * h[0], m["min"][1] + (j + 0.5) * h[1], m["min"][2] + (k + 0.5) * h[2],
+                         rep.time, R, G, R / G])
+        Rprev = (T - T0) / rep.deltaT
+        snaps = [T]
+    got = o.solidification_events()
+    assert len(got) > 50, len(got)
+    interior = np.array([e for e in got if m["min"][0] + h[0] < e[0] < m["max"][0] - h[0] and m["min"][1] + h[1] < e[1] < m["max"][1] - h[1]
+                         and m["min"][2] + h[2] < e[2] < m["max"][2] - h[2]])
+    want = np.array(want)
+    assert interior.shape == want.shape and len(want) > 20
+    assert np.allclose(interior[:, :4], want[:, :4], rtol=1e-12, atol=0)
+    assert np.allclose(interior[:, 4:], want[:, 4:], rtol=1e-9)
+    assert np.all(got[:, 4] > 0) and np.all(np.diff(got[:, 3]) >= 0)    # cooling rates known by then; append order is by time
+    o.close()
+
+
+def test_solidification_box_and_decomposition(oracle):
+    """setOverlapCells (solidificationData.C:99-131): only cells whose bounding box touches the box record events; the union
+    of the per-rank event lists of a decomposed run is the serial list."""
+    case = cases.amb2018_02_b(n=(75, 13, 8))
+    box = ([0.0004, -1, -1], [0.0012, 1, 1])
+    a, b = ol.OracleCase(case, lib=oracle), ol.OracleCase(case, ranks=2, lib=oracle)
+    for o in (a, b):
+        o.solidification_enable(box[0], box[1], 1620.0)
+    for _ in range(220):
+        a.step(); b.step()
+    ea, eb = a.solidification_events(), b.solidification_events()
+    dx = 0.003 / 75
+    assert len(ea) > 10 and ea[:, 0].min() >= 0.0004 - dx and ea[:, 0].max() <= 0.0012 + dx
+    assert len(ea) == len(eb)
+    key = lambda e: np.lexsort((e[:, 0], e[:, 1], e[:, 2], e[:, 3]))
+    assert np.allclose(ea[key(ea)], eb[key(eb)], rtol=1e-9)
+    a.close(); b.close()

@@ -25,18 +25,25 @@ n = (48, 14, 11)
 kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC) if mode == "implicit" else dict()
 if mode == "bicg":
     kw = dict(explicitSolve=0, maxDi=10.0)
+SOLID_ISO, ISO = 1500.0, [1620.0, 1410.0, 600.0]
+if mode == "funcobj":      # two z layers: every cell touches the slab interface, so the function objects cross processor faces
+    n, SOLID_ISO, ISO = (48, 14, 2), 600.0, [900.0, 600.0, 400.0]
 case = cases.amb2018_02_b(n=n, **kw)
 g = lib.Case(ctx, case)
+SBOX = ([-1, -1, -1], [1, 1, 1])
+g.solidification_enable(SBOX[0], SBOX[1], SOLID_ISO)
 assert g.n_local == partition.local_cells(n, rank, world)
 reps = [g.step() for _ in range(steps)]
 T = partition.gather_field(g.field(abi.FIELD_T), n, rank, world, dist, device="cuda")
 A = partition.gather_field(g.field(abi.FIELD_ALPHA_SOLID), n, rank, world, dist, device="cuda")
-ISO = [1620.0, 1410.0, 600.0]
 mp = g.melt_pool_dimensions(ISO, 30.0)     # collective
+evs = [None] * world
+dist.all_gather_object(evs, g.solidification_events())
 ok = True
 if rank == 0:
     import oracle_lib as ol
     o = ol.OracleCase(case, ranks=world)
+    o.solidification_enable(SBOX[0], SBOX[1], SOLID_ISO)
     oreps = [o.step() for _ in range(steps)]
     To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
     eT = float(np.max(np.abs(T - To)) / np.max(np.abs(To)))
@@ -45,8 +52,12 @@ if rank == 0:
     dts = max(abs(a.deltaT - b.deltaT) / b.deltaT for a, b in zip(reps, oreps))
     mpo = o.melt_pool_dimensions(ISO, 30.0)
     eM = float(np.max(np.abs(mp - mpo)) / max(np.max(np.abs(mpo)), 1e-300))
-    ok = eT < 1e-9 and eA < 1e-9 and its <= 1 and dts < 1e-10 and eM < 1e-9 and mpo[2].max() > 0
-    print(f"MULTI {mode} ranks={world} relLinf(T)={eT:.3e} Linf(alpha)={eA:.3e} iterdiff={its} dtdiff={dts:.2e} meltPool={eM:.2e} Tmax={To.max():.1f} "
+    ev, evo = np.concatenate(evs), o.solidification_events()
+    okS = ev.shape == evo.shape and np.array_equal(ev[:, :3], evo[:, :3]) and np.allclose(ev[:, 3:], evo[:, 3:], rtol=1e-6)
+    ok = eT < 1e-9 and eA < 1e-9 and its <= 1 and dts < 1e-10 and eM < 1e-9 and mpo[2].max() > 0 and okS
+    if mode == "funcobj":
+        ok = ok and len(evo) > 20 and mpo.min() > 0
+    print(f"MULTI {mode} ranks={world} relLinf(T)={eT:.3e} Linf(alpha)={eA:.3e} iterdiff={its} dtdiff={dts:.2e} meltPool={eM:.2e} solidEvents={len(evo)}/{'same' if okS else 'DIFF'} Tmax={To.max():.1f} "
           f"{'OK' if ok else 'FAIL'}", flush=True)
 g.close(); ctx.close()
 dist.barrier()
