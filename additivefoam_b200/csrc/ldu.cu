@@ -286,7 +286,7 @@ void Ldu::ensureWave(bool dilu)
 }
 
 // op: 0 factor (after the gather), 1 forward, 2 backward
-void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
+void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio)
 {
     WaveArgs a;
     a.g = wave_geom(dims);
@@ -315,10 +315,11 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
     static const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : 2; }();
     const bool oneWarp = forced ? forced == 1 : a.g.nTiles > 1536;
     if (oneWarp) {
-        if (op == 0) { if (dilu) k_wave<0, true, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false><<<grid, 32, 0, s>>>(a); }
-        else if (op == 1) k_wave<1, false, false><<<grid, 32, 0, s>>>(a);
-        else if (dot) k_wave<2, false, true><<<grid, 32, 0, s>>>(a);
-        else k_wave<2, false, false><<<grid, 32, 0, s>>>(a);
+        if (op == 0) { if (dilu) k_wave<0, true, false, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false, false><<<grid, 32, 0, s>>>(a); }
+        else if (op == 1) { if (wio) k_wave<1, false, false, true><<<grid, 32, 0, s>>>(a); else k_wave<1, false, false, false><<<grid, 32, 0, s>>>(a); }
+        else if (wio) { if (dot) k_wave<2, false, true, true><<<grid, 32, 0, s>>>(a); else k_wave<2, false, false, true><<<grid, 32, 0, s>>>(a); }
+        else if (dot) k_wave<2, false, true, false><<<grid, 32, 0, s>>>(a);
+        else k_wave<2, false, false, false><<<grid, 32, 0, s>>>(a);
     } else {
         auto launch = [&](auto kernel, size_t shm) {
             static std::set<const void*> configured;     // every k_wave2 instantiation has the same pointer type
@@ -326,10 +327,11 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA)
                 B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
             kernel<<<grid, 64, shm, s>>>(a);
         };
-        if (op == 0) { if (dilu) launch(k_wave2<0, true, false>, sizeof(WaveSmem<0, true>)); else launch(k_wave2<0, false, false>, sizeof(WaveSmem<0, false>)); }
-        else if (op == 1) launch(k_wave2<1, false, false>, sizeof(WaveSmem<1, false>));
-        else if (dot) launch(k_wave2<2, false, true>, sizeof(WaveSmem<2, false>));
-        else launch(k_wave2<2, false, false>, sizeof(WaveSmem<2, false>));
+        if (op == 0) { if (dilu) launch(k_wave2<0, true, false, false>, sizeof(WaveSmem<0, true, false>)); else launch(k_wave2<0, false, false, false>, sizeof(WaveSmem<0, false, false>)); }
+        else if (op == 1) { if (wio) launch(k_wave2<1, false, false, true>, sizeof(WaveSmem<1, false, true>)); else launch(k_wave2<1, false, false, false>, sizeof(WaveSmem<1, false, false>)); }
+        else if (wio) { if (dot) launch(k_wave2<2, false, true, true>, sizeof(WaveSmem<2, false, true>)); else launch(k_wave2<2, false, false, true>, sizeof(WaveSmem<2, false, true>)); }
+        else if (dot) launch(k_wave2<2, false, true, false>, sizeof(WaveSmem<2, false, false>));
+        else launch(k_wave2<2, false, false, false>, sizeof(WaveSmem<2, false, false>));
     }
     B200_LAUNCH_CHECK();
     if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }
@@ -365,7 +367,7 @@ void Ldu::factor(int kind, const MatrixView& A)
                 B200_LAUNCH_CHECK();
                 waveEpoch = A.offDiagEpoch; waveUpper = A.upper; waveLower = A.lower; waveDilu = dilu;
             }
-            waveSweep(0, dilu, false, A.diag, nullptr);
+            waveSweep(0, dilu, false, A.diag, nullptr, false);
             return;          // rD lives in wave order (A0)
         } else if (isBlock) {
             if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
@@ -380,7 +382,7 @@ void Ldu::factor(int kind, const MatrixView& A)
 }
 
 // wA = M^-1 rA, optionally with sum(wA . dotVec) into slot S_RHO
-void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int doDot, const double* dotVec)
+void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int doDot, const double* dotVec, bool wio)
 {
     cudaStream_t s = ctx->stream;
     const SolveState* st = d_state;
@@ -390,8 +392,8 @@ void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* 
     const bool dilu = kind == 3;
     const double* nul = nullptr;
     if (isBlock && useWave) {
-        { ProfScope ps_(ctx, PC_SWEEP_FWD); waveSweep(1, dilu, false, rA, wA); }
-        { ProfScope ps_(ctx, PC_SWEEP_BWD); waveSweep(2, dilu, doDot != 0, rA, wA); }
+        { ProfScope ps_(ctx, PC_SWEEP_FWD); waveSweep(1, dilu, false, rA, wA, wio); }
+        { ProfScope ps_(ctx, PC_SWEEP_BWD); waveSweep(2, dilu, doDot != 0, rA, wA, wio); }
         B200_CHECK(!doDot || dotVec == rA, "fused preconditioner dot product is defined against rA");
     } else if (isBlock) {
         const int64_t work_ = (int64_t)dims.ny * dims.nz;
@@ -415,7 +417,7 @@ void Ldu::precondition(int kind, const MatrixView& A, const double* rA, double* 
     ensureWork();
     B200_CUDA(cudaMemsetAsync(d_state, 0, sizeof(SolveState), ctx->stream));
     factor(kind, A);
-    applyPrecond(kind, A, rA, wA, 0, nullptr);
+    applyPrecond(kind, A, rA, wA, 0, nullptr, false);
 }
 
 // ------------------------------------------------------------------ Krylov drivers
@@ -489,6 +491,28 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     allreduce(S_NORM, 2);
     ctrl(*this, C_INIT);
     factor(sc.precond, A);
+    // PCG with a DIC/DILU wave sweep keeps the residual (RF) and the preconditioned residual (WB) in wave order: the sweeps
+    // then stream whole rows only, and the two vector updates transpose through shared memory (wave_kernels.cuh)
+    static const bool wioOff = [] { const char* e = std::getenv("B200_WAVE_IO"); return e && std::string(e) == "natural"; }();
+    const bool wio = pcg && isBlock && useWave && sc.precond >= 2 && !wioOff;
+    WaveGeom wg{};
+    int wioGrid = 1;
+    if (wio) {
+        wg = wave_geom(dims);
+        const int64_t items = (int64_t)wg.nTiles * ((wg.nStepsPad + TCH - 1) / TCH);
+        static int perSM = 0;            // resident blocks of the least-occupant of the three kernels: a persistent grid of exactly that size
+        if (!perSM) {
+            int a = 0, b = 0, c = 0;
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_wave_pcg_update, 256, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_wave_pcg_p, 256, 0));
+            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_wave_from_natural, 256, 0));
+            perSM = std::max(1, std::min(a, std::min(b, c)));
+        }
+        wioGrid = (int)std::max<int64_t>(1, std::min<int64_t>(items, (int64_t)ctx->smCount * perSM));
+        wioGrid = std::min(wioGrid, RED_MAX_BLOCKS);
+        ProfScope ps_(ctx, PC_VECTOR);
+        k_wave_from_natural<<<wioGrid, 256, 0, s>>>(wg, rA, wave[8], st); B200_LAUNCH_CHECK();
+    }
     if (!pcg) { { ProfScope ps_(ctx, PC_VECTOR); k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); } }
 
     const int hardMax = std::max(sc.maxIter + 1, sc.minIter);
@@ -499,14 +523,20 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     for (;;) {
         for (int it = 0; it < chunk && enqueued < hardMax; it++, enqueued++) {
             if (pcg) {
-                applyPrecond(sc.precond, A, rA, wA, 1, rA);         // wA = M^-1 rA ; wArA
+                applyPrecond(sc.precond, A, rA, wA, 1, rA, wio);    // wA = M^-1 rA ; wArA
                 allreduce(S_RHO, 1);
                 ctrl(*this, C_PCG_BETA);
-                { ProfScope ps_(ctx, PC_VECTOR); k_pcg_p<<<redBlocks, BLK, 0, s>>>(n, wA, pA, st); B200_LAUNCH_CHECK(); }
+                { ProfScope ps_(ctx, PC_VECTOR);
+                  if (wio) k_wave_pcg_p<<<wioGrid, 256, 0, s>>>(wg, wave[9], pA, st);
+                  else k_pcg_p<<<redBlocks, BLK, 0, s>>>(n, wA, pA, st);
+                  B200_LAUNCH_CHECK(); }
                 amulFused(A, pA, qA, AM_DOT_YX, nullptr);           // q = A pA ; wApA
                 allreduce(S_DEN, 1);
                 ctrl(*this, C_PCG_ALPHA);
-                { ProfScope ps_(ctx, PC_VECTOR); k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, red, st); B200_LAUNCH_CHECK(); }
+                { ProfScope ps_(ctx, PC_VECTOR);
+                  if (wio) k_wave_pcg_update<<<wioGrid, 256, 0, s>>>(wg, pA, qA, psi, wave[8], red, st);
+                  else k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, red, st);
+                  B200_LAUNCH_CHECK(); }
                 allreduce(S_MAGR, 1);
                 ctrl(*this, C_ITER_END);
             } else {
@@ -514,7 +544,7 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
                 allreduce(S_RHO, 1);
                 ctrl(*this, C_BICG_RHO);
                 { ProfScope ps_(ctx, PC_VECTOR); k_bicg_p<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, pA, st); B200_LAUNCH_CHECK(); }
-                applyPrecond(sc.precond, A, pA, yA, 0, nullptr);
+                applyPrecond(sc.precond, A, pA, yA, 0, nullptr, false);
                 amulFused(A, yA, AyA, AM_DOT_AUXY, rA0);            // rA0 . AyA
                 allreduce(S_DEN, 1);
                 ctrl(*this, C_BICG_ALPHA);
@@ -523,7 +553,7 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
                 ctrl(*this, C_BICG_SCHECK);
                 { ProfScope ps_(ctx, PC_VECTOR); k_bicg_early<<<redBlocks, BLK, 0, s>>>(n, yA, psi, st, &d_state->early); B200_LAUNCH_CHECK(); }
                 ctrl(*this, C_BICG_EARLY_END);
-                applyPrecond(sc.precond, A, sA, zA, 0, nullptr);
+                applyPrecond(sc.precond, A, sA, zA, 0, nullptr, false);
                 amulFused(A, zA, tA, AM_TT_TS, sA);                 // tA.tA, tA.sA
                 allreduce(S_TT, 2);
                 ctrl(*this, C_BICG_OMEGA);

@@ -124,12 +124,12 @@ public:
     int64_t waveLen = 0;
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
     void ensureWave(bool dilu);
-    void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA);
+    void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio);
 
     void ensureWork();
     double* vec(int i) { return work[i] + ghost; }
     void factor(int kind, const MatrixView& A);
-    void applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int dotMode, const double* dotVec);
+    void applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int dotMode, const double* dotVec, bool wio);
     void amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux);
     void exchange(const double* x);   // interface / ghost-plane update before an Amul on x
     void allreduce(int slot0, int n);
