@@ -117,7 +117,7 @@ Ldu::~Ldu()
     for (auto& p : stage) dev_free(p);
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder);
 }
 
 void Ldu::setBlock(int nx, int ny, int nz)
@@ -282,7 +282,27 @@ void Ldu::ensureWave(bool dilu)
     const int nArr = dilu ? 13 : 10;
     for (int q = 0; q < nArr; q++)
         if (!wave[q]) { wave[q] = dev_alloc<double>((size_t)waveLen); B200_CUDA(cudaMemsetAsync(wave[q], 0, (size_t)waveLen * sizeof(double), ctx->stream)); }
-    if (!waveFlags) { waveFlags = dev_alloc<int>(4); wavePartial = dev_alloc<double>(g.nTiles); }
+    if (!waveFlags) {
+        waveFlags = dev_alloc<int>(4); wavePartial = dev_alloc<double>(g.nTiles);
+        // Tiles are handed out along the wavefront, not row by row.  Tile (J, K) can run only a fixed number of steps behind
+        // (J-1, K) and (J, K-1) (the lane skew of the tile edge plus the look-ahead of the loads, ~15 and ~11 steps, plus the
+        // store-to-poll latency), so its earliest start is about 9J + 7K in those units.  Handing tiles out in that order keeps
+        // the resident ones within a fraction of a tile length of each other; in row-major order a row of 50 tiles alone spans
+        // more than the ~1000 steps of a tile, and most resident warps would sit waiting for their upstream neighbour.  Any
+        // order increasing in both J and K is topological, which is all the deadlock argument needs.
+        std::vector<int> order(g.nTiles);
+        for (int t = 0; t < g.nTiles; t++) order[t] = t;
+        const int nJ = g.nJ;
+        static const int wJ = [] { const char* e = std::getenv("B200_WAVE_ORDER_J"); return e ? std::atoi(e) : 9; }();
+        static const int wK = [] { const char* e = std::getenv("B200_WAVE_ORDER_K"); return e ? std::atoi(e) : 7; }();
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+            const long kx = (long)wJ * (x % nJ) + (long)wK * (x / nJ), ky = (long)wJ * (y % nJ) + (long)wK * (y / nJ);
+            return kx < ky;
+        });
+        waveOrder = dev_alloc<int>(g.nTiles);
+        B200_CUDA(cudaMemcpyAsync(waveOrder, order.data(), sizeof(int) * g.nTiles, cudaMemcpyHostToDevice, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));        // `order` is a local
+    }
 }
 
 // op: 0 factor (after the gather), 1 forward, 2 backward
@@ -293,7 +313,7 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
     a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12];
     a.rA = rA; a.wA = wA;
-    a.ticket = waveFlags; a.tilePartial = wavePartial; a.st = d_state;
+    a.ticket = waveFlags; a.order = waveOrder; a.tilePartial = wavePartial; a.st = d_state;
     {
         // keep what the resident tiles have prefetched but not yet consumed well inside L2 (126 MB): about 32 MB in flight
         const int64_t resident = std::min<int64_t>(a.g.nTiles, (int64_t)ctx->smCount * 12);
@@ -309,11 +329,11 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     // WF and WB for the substitution sweeps, which then re-arm each other's array as they go
     if (op == 0) B200_CUDA(cudaMemsetAsync(wave[8], 0xFF, (size_t)waveLen * sizeof(double), s));
     const int grid = a.g.nTiles;
-    // Two implementations of the same sweep (bit-identical results).  Few tiles (a thin slab: ~3 warps per SM) => the sweep
-    // is bound by the dependency chain and the warp-specialised kernel (memory warp + compute warp) is ahead; many tiles =>
-    // it is bound by HBM and the one-warp kernel, which keeps more tiles in flight per SM, is ahead.  B200_WAVE overrides.
-    static const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : 2; }();
-    const bool oneWarp = forced ? forced == 1 : a.g.nTiles > 1536;
+    // Two implementations of the same sweep (bit-identical results): the warp-specialised kernel (memory warp + compute warp
+    // per tile) is the default at every size now that tiles are handed out along the wavefront; the one-warp kernel stays
+    // selectable (B200_WAVE=1warp) as the reference point the profiles compare against.
+    const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : 2; }();
+    const bool oneWarp = forced == 1;
     if (oneWarp) {
         if (op == 0) { if (dilu) k_wave<0, true, false, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false, false><<<grid, 32, 0, s>>>(a); }
         else if (op == 1) { if (wio) k_wave<1, false, false, true><<<grid, 32, 0, s>>>(a); else k_wave<1, false, false, false><<<grid, 32, 0, s>>>(a); }
@@ -327,11 +347,26 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
                 B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
             kernel<<<grid, 64, shm, s>>>(a);
         };
-        if (op == 0) { if (dilu) launch(k_wave2<0, true, false, false>, sizeof(WaveSmem<0, true, false>)); else launch(k_wave2<0, false, false, false>, sizeof(WaveSmem<0, false, false>)); }
-        else if (op == 1) { if (wio) launch(k_wave2<1, false, false, true>, sizeof(WaveSmem<1, false, true>)); else launch(k_wave2<1, false, false, false>, sizeof(WaveSmem<1, false, false>)); }
-        else if (wio) { if (dot) launch(k_wave2<2, false, true, true>, sizeof(WaveSmem<2, false, true>)); else launch(k_wave2<2, false, false, true>, sizeof(WaveSmem<2, false, true>)); }
-        else if (dot) launch(k_wave2<2, false, true, false>, sizeof(WaveSmem<2, false, false>));
-        else launch(k_wave2<2, false, false, false>, sizeof(WaveSmem<2, false, false>));
+        // ring geometry: few tiles => deep slots (latency of the chain); many tiles => small slots, more CTAs per SM
+        const char* eg = std::getenv("B200_WAVE2_RING");
+        // many tiles: 3 slots -> 4 CTAs per SM keep HBM busy; few tiles (thin slab, latency-bound): 6 slots of look-ahead
+        const int cfg = eg ? std::atoi(eg) : (a.g.nTiles > 1536 ? 83 : 86);
+#define B200_W2(G_, R_)                                                                                                                        \
+        do {                                                                                                                                   \
+            if (op == 0) { if (dilu) launch(k_wave2<0, true, false, false, G_, R_>, sizeof(WaveSmem<0, true, false, G_, R_>));                    \
+                           else launch(k_wave2<0, false, false, false, G_, R_>, sizeof(WaveSmem<0, false, false, G_, R_>)); }                     \
+            else if (op == 1) { if (wio) launch(k_wave2<1, false, false, true, G_, R_>, sizeof(WaveSmem<1, false, true, G_, R_>));                \
+                                else launch(k_wave2<1, false, false, false, G_, R_>, sizeof(WaveSmem<1, false, false, G_, R_>)); }                \
+            else if (wio) { if (dot) launch(k_wave2<2, false, true, true, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>));                     \
+                            else launch(k_wave2<2, false, false, true, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>)); }                      \
+            else if (dot) launch(k_wave2<2, false, true, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                              \
+            else launch(k_wave2<2, false, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                                      \
+        } while (0)
+        if (cfg == 44) B200_W2(4, 4);
+        else if (cfg == 83) B200_W2(8, 3);
+        else if (cfg == 86) B200_W2(8, 6);
+        else B200_W2(8, 4);
+#undef B200_W2
     }
     B200_LAUNCH_CHECK();
     if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }

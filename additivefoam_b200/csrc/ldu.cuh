@@ -120,6 +120,7 @@ public:
     bool useWave = true;
     double* wave[13] = {nullptr};    // A0 PX PY PZ QX QY QZ WF RF WB NX NY NZ
     int* waveFlags = nullptr;        // tile ticket
+    int* waveOrder = nullptr;        // ticket -> tile
     double* wavePartial = nullptr;
     int64_t waveLen = 0;
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
