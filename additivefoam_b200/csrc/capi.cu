@@ -322,6 +322,14 @@ int b200_case_solidification_events(b200_case* c, double* events, int64_t maxEve
     *nRecorded = c->p->solidificationEvents(events, maxEvents);
     B200_CATCH
 }
+int b200_selftest_division(b200_ctx* ctx, int64_t nPairs, int64_t seed, int32_t expRange, int64_t* mismatches)
+{
+    B200_TRY
+    B200_CHECK(ctx && mismatches && nPairs >= 0 && expRange >= 0 && expRange <= 1000, "selftest_division: bad arguments");
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    *mismatches = (int64_t)selftest_division(ctx->p, (unsigned long long)nPairs, (unsigned long long)seed, expRange);
+    B200_CATCH
+}
 int b200_case_kernel_launches(b200_case*, int64_t* launches)
 {
     *launches = g_launches;

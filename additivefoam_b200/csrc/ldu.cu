@@ -279,11 +279,11 @@ void Ldu::ensureWave(bool dilu)
 {
     const WaveGeom g = wave_geom(dims);
     waveLen = (int64_t)g.nTiles * g.nStepsPad * 32;
-    const int nArr = dilu ? 13 : 10;
-    for (int q = 0; q < nArr; q++)
-        if (!wave[q]) { wave[q] = dev_alloc<double>((size_t)waveLen); B200_CUDA(cudaMemsetAsync(wave[q], 0, (size_t)waveLen * sizeof(double), ctx->stream)); }
+    for (int q = 0; q < 14; q++)
+        if (!wave[q] && (q < 10 || q == 13 || dilu)) { wave[q] = dev_alloc<double>((size_t)waveLen); B200_CUDA(cudaMemsetAsync(wave[q], 0, (size_t)waveLen * sizeof(double), ctx->stream)); }
     if (!waveFlags) {
         waveFlags = dev_alloc<int>(4); wavePartial = dev_alloc<double>(g.nTiles);
+        B200_CUDA(cudaMemsetAsync(waveFlags, 0, 4 * sizeof(int), ctx->stream));     // [0] tile ticket, [1] redo exactly, [2] veto, [3] block count
         // Tiles are handed out along the wavefront, not row by row.  Tile (J, K) can run only a fixed number of steps behind
         // (J-1, K) and (J, K-1) (the lane skew of the tile edge plus the look-ahead of the loads, ~15 and ~11 steps, plus the
         // store-to-poll latency), so its earliest start is about 9J + 7K in those units.  Handing tiles out in that order keeps
@@ -305,13 +305,29 @@ void Ldu::ensureWave(bool dilu)
     }
 }
 
+// persistent grid of the transposing vector kernels (wave_kernels.cuh): exactly what is resident
+int Ldu::waveVecGrid()
+{
+    static int perSM = 0;
+    if (!perSM) {
+        int a = 0, b = 0, c = 0;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_wave_pcg_update, 256, 0));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_wave_pcg_p, 256, 0));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_wave_from_natural, 256, 0));
+        perSM = std::max(1, std::min(a, std::min(b, c)));
+    }
+    const WaveGeom g = wave_geom(dims);
+    const int64_t items = (int64_t)g.nTiles * ((g.nStepsPad + TCH - 1) / TCH);
+    return (int)std::min<int64_t>(std::max<int64_t>(1, std::min<int64_t>(items, (int64_t)ctx->smCount * perSM)), RED_MAX_BLOCKS);
+}
+
 // op: 0 factor (after the gather), 1 forward, 2 backward
 void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio)
 {
     WaveArgs a;
     a.g = wave_geom(dims);
     a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
-    a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12];
+    a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.DG = wave[13];
     a.rA = rA; a.wA = wA;
     a.ticket = waveFlags; a.order = waveOrder; a.tilePartial = wavePartial; a.st = d_state;
     {
@@ -324,7 +340,7 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         a.pfGroups = e ? std::atoi(e) : pf;
     }
     cudaStream_t s = ctx->stream;
-    B200_CUDA(cudaMemsetAsync(waveFlags, 0, sizeof(int), s));
+    B200_CUDA(cudaMemsetAsync(waveFlags, 0, (op == 0 ? 2 : 1) * sizeof(int), s));      // tile ticket (+ the factor sweep's out-of-range report)
     // the factor sweep exchanges raw rD through RF: arm it with the sentinel (all-ones NaN); the factor sweep itself arms
     // WF and WB for the substitution sweeps, which then re-arm each other's array as they go
     if (op == 0) B200_CUDA(cudaMemsetAsync(wave[8], 0xFF, (size_t)waveLen * sizeof(double), s));
@@ -334,6 +350,9 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     // selectable (B200_WAVE=1warp) as the reference point the profiles compare against.
     const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : 2; }();
     const bool oneWarp = forced == 1;
+    if (op == 0 && !oneWarp) {      // the warp-specialised factor sweep streams the diagonal from wave order as well
+        k_wave_from_natural<<<waveVecGrid(), 256, 0, s>>>(a.g, rA, wave[13], 1.0, d_state); B200_LAUNCH_CHECK();
+    }
     if (oneWarp) {
         if (op == 0) { if (dilu) k_wave<0, true, false, false><<<grid, 32, 0, s>>>(a); else k_wave<0, false, false, false><<<grid, 32, 0, s>>>(a); }
         else if (op == 1) { if (wio) k_wave<1, false, false, true><<<grid, 32, 0, s>>>(a); else k_wave<1, false, false, false><<<grid, 32, 0, s>>>(a); }
@@ -353,20 +372,27 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         const int cfg = eg ? std::atoi(eg) : (a.g.nTiles > 1536 ? 83 : 86);
 #define B200_W2(G_, R_)                                                                                                                        \
         do {                                                                                                                                   \
-            if (op == 0) { if (dilu) launch(k_wave2<0, true, false, false, G_, R_>, sizeof(WaveSmem<0, true, false, G_, R_>));                    \
-                           else launch(k_wave2<0, false, false, false, G_, R_>, sizeof(WaveSmem<0, false, false, G_, R_>)); }                     \
-            else if (op == 1) { if (wio) launch(k_wave2<1, false, false, true, G_, R_>, sizeof(WaveSmem<1, false, true, G_, R_>));                \
-                                else launch(k_wave2<1, false, false, false, G_, R_>, sizeof(WaveSmem<1, false, false, G_, R_>)); }                \
-            else if (wio) { if (dot) launch(k_wave2<2, false, true, true, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>));                     \
-                            else launch(k_wave2<2, false, false, true, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>)); }                      \
-            else if (dot) launch(k_wave2<2, false, true, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                              \
-            else launch(k_wave2<2, false, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                                      \
+            if (op == 0) { if (dilu) launch(k_wave2<0, true, false, true, true, G_, R_>, sizeof(WaveSmem<0, true, true, G_, R_>));                      \
+                           else launch(k_wave2<0, false, false, true, true, G_, R_>, sizeof(WaveSmem<0, false, true, G_, R_>)); }                       \
+            else if (op == 1) { if (wio) launch(k_wave2<1, false, false, true, false, G_, R_>, sizeof(WaveSmem<1, false, true, G_, R_>));                \
+                                else launch(k_wave2<1, false, false, false, false, G_, R_>, sizeof(WaveSmem<1, false, false, G_, R_>)); }                \
+            else if (wio) { if (dot) launch(k_wave2<2, false, true, true, false, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>));                     \
+                            else launch(k_wave2<2, false, false, true, false, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>)); }                      \
+            else if (dot) launch(k_wave2<2, false, true, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                              \
+            else launch(k_wave2<2, false, false, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                                      \
         } while (0)
         if (cfg == 44) B200_W2(4, 4);
         else if (cfg == 83) B200_W2(8, 3);
         else if (cfg == 86) B200_W2(8, 6);
         else B200_W2(8, 4);
 #undef B200_W2
+        if (op == 0) {
+            // the exact factor sweep (plain FP64 operators) behind the fast one: both kernels return at once unless the fast
+            // sweep was vetoed by the coefficients or reported a diagonal entry outside its exponent range
+            k_wave_refactor_prepare<<<ctx->smCount * 4, 256, 0, s>>>(a, waveLen);
+            if (dilu) launch(k_wave2<0, true, false, true, false, 8, 4>, sizeof(WaveSmem<0, true, true, 8, 4>));
+            else launch(k_wave2<0, false, false, true, false, 8, 4>, sizeof(WaveSmem<0, false, true, 8, 4>));
+        }
     }
     B200_LAUNCH_CHECK();
     if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }
@@ -395,6 +421,8 @@ void Ldu::factor(int kind, const MatrixView& A)
                 a.g = wave_geom(dims);
                 a.A0 = wave[0]; a.PX = wave[1]; a.PY = wave[2]; a.PZ = wave[3]; a.QX = wave[4]; a.QY = wave[5]; a.QZ = wave[6];
                 a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.st = st;
+                a.ticket = waveFlags;
+                B200_CUDA(cudaMemsetAsync(waveFlags + 2, 0, sizeof(int), s));      // the veto of the fast factor sweep belongs to the off-diagonals
                 const int64_t rows = (int64_t)a.g.nTiles * a.g.nStepsPad;
                 const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->smCount * 16));
                 if (dilu) k_wave_gather<true><<<grid, 256, 0, s>>>(dims, a, A.upper, A.lower);
@@ -534,19 +562,9 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     int wioGrid = 1;
     if (wio) {
         wg = wave_geom(dims);
-        const int64_t items = (int64_t)wg.nTiles * ((wg.nStepsPad + TCH - 1) / TCH);
-        static int perSM = 0;            // resident blocks of the least-occupant of the three kernels: a persistent grid of exactly that size
-        if (!perSM) {
-            int a = 0, b = 0, c = 0;
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_wave_pcg_update, 256, 0));
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_wave_pcg_p, 256, 0));
-            B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c, k_wave_from_natural, 256, 0));
-            perSM = std::max(1, std::min(a, std::min(b, c)));
-        }
-        wioGrid = (int)std::max<int64_t>(1, std::min<int64_t>(items, (int64_t)ctx->smCount * perSM));
-        wioGrid = std::min(wioGrid, RED_MAX_BLOCKS);
+        wioGrid = waveVecGrid();
         ProfScope ps_(ctx, PC_VECTOR);
-        k_wave_from_natural<<<wioGrid, 256, 0, s>>>(wg, rA, wave[8], st); B200_LAUNCH_CHECK();
+        k_wave_from_natural<<<wioGrid, 256, 0, s>>>(wg, rA, wave[8], 0.0, st); B200_LAUNCH_CHECK();
     }
     if (!pcg) { { ProfScope ps_(ctx, PC_VECTOR); k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); } }
 
@@ -605,6 +623,19 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     perf.initialResidual = h_state->initRes; perf.finalResidual = h_state->finalRes;
     perf.nIterations = h_state->nIter; perf.converged = h_state->converged; perf.singular = h_state->singular;
     return perf;
+}
+
+unsigned long long selftest_division(Ctx* ctx, unsigned long long n, unsigned long long seed, int expRange)
+{
+    unsigned long long* d = dev_alloc<unsigned long long>(1);
+    unsigned long long h = 0;
+    B200_CUDA(cudaMemsetAsync(d, 0, sizeof(h), ctx->stream));
+    k_selftest_division<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(n, seed, expRange, d);
+    B200_LAUNCH_CHECK();
+    d2h(&h, d, 1, ctx->stream);
+    ctx->sync();
+    dev_free(d);
+    return h;
 }
 
 } // namespace b200

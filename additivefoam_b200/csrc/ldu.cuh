@@ -118,7 +118,7 @@ public:
     int redBlocks = 1;
     // tile-wavefront sweeps (block addressing): coefficient arrays renumbered into wave order
     bool useWave = true;
-    double* wave[13] = {nullptr};    // A0 PX PY PZ QX QY QZ WF RF WB NX NY NZ
+    double* wave[14] = {nullptr};    // A0 PX PY PZ QX QY QZ WF RF WB NX NY NZ DG
     int* waveFlags = nullptr;        // tile ticket
     int* waveOrder = nullptr;        // ticket -> tile
     double* wavePartial = nullptr;
@@ -126,6 +126,7 @@ public:
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
     void ensureWave(bool dilu);
     void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio);
+    int waveVecGrid();
 
     void ensureWork();
     double* vec(int i) { return work[i] + ghost; }
@@ -135,5 +136,8 @@ public:
     void exchange(const double* x);   // interface / ghost-plane update before an Amul on x
     void allreduce(int slot0, int n);
 };
+
+// wave_kernels.cuh's shared-reciprocal division against the compiler's operator on n pseudo-random pairs; returns the mismatches
+unsigned long long selftest_division(Ctx* ctx, unsigned long long n, unsigned long long seed, int expRange);
 
 } // namespace b200

@@ -29,7 +29,7 @@ SYMBOLS = [
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
     "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_solidification_enable",
-    "b200_case_solidification_events", "b200_case_kernel_launches",
+    "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse",
 ]
 
@@ -105,6 +105,7 @@ def load():
     L.b200_case_melt_pool_dimensions.argtypes = [vp, C.c_int32, dp, C.c_double, dp]
     L.b200_case_solidification_enable.argtypes = [vp, dp, dp, C.c_double, C.c_int64]
     L.b200_case_solidification_events.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
+    L.b200_selftest_division.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
     L.b200_case_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.b200_scan_path_parse.argtypes = [C.c_char_p, dp, C.c_int32]
     _lib = L
@@ -179,6 +180,11 @@ class Context:
         cnt = (C.c_int64 * n)()
         _check(self.L.b200_profile_read(self.h, ms, cnt, n))
         return {self.L.b200_profile_name(i).decode(): (ms[i], cnt[i]) for i in range(n)}
+
+    def selftest_division(self, n_pairs, seed=1, exp_range=250):
+        bad = C.c_int64()
+        _check(self.L.b200_selftest_division(self.h, int(n_pairs), int(seed), int(exp_range), C.byref(bad)))
+        return bad.value
 
     def kernel_launches(self):
         n = C.c_int64()

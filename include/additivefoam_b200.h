@@ -259,6 +259,11 @@ int  b200_case_solidification_enable(b200_case* c, const double boxMin[3], const
 /* Copies this rank's events, in the reference's append order (time step, then cell), into events[maxEvents][7] (may be NULL to
  * query).  *nRecorded = events seen so far; a value above the capacity given at enable means the excess was dropped. */
 int  b200_case_solidification_events(b200_case* c, double* events, int64_t maxEvents, int64_t* nRecorded);
+/* Diagnostic: the DIC/DILU factor sweep divides with a reciprocal refinement shared between the three quotients of one
+ * diagonal entry ([UPSTREAM] DICPreconditioner::calcReciprocalD's `upper*upper/rD`); this runs that sequence against the
+ * compiler's FP64 division on nPairs pseudo-random operand pairs with exponents in +-expRange and returns the number of
+ * bit patterns that differ (0 inside the range the sweep uses it for, +-250). */
+int  b200_selftest_division(b200_ctx* ctx, int64_t nPairs, int64_t seed, int32_t expRange, int64_t* mismatches);
 /* Device time (ms) spent in the kernels of the last step by group, for the benchmark:
  * [0] properties+dt numbers, [1] heat source, [2] assembly, [3] corrector fold+alpha update,
  * [4] Krylov solve. */

@@ -129,3 +129,44 @@ def test_set_block_rejects_wrong_addressing(ctx):
         lib._check(s.L.b200_ldu_set_block(s.h, 5, 6, 4))
     lib._check(s.L.b200_ldu_set_block(s.h, 6, 5, 4))
     s.close()
+
+
+def test_shared_reciprocal_division_is_the_compilers_division(ctx):
+    """The factor sweep forms upper*upper/rD with one reciprocal refinement per rD entry (wave_kernels.cuh: div_refine, div_by).
+    That is nvcc's own fast path for a/b split in two, so every quotient must carry the bit pattern of the operator -- checked
+    here on 2^32 pseudo-random operand pairs over the exponent range the sweep uses it for, and on a narrow range around 1."""
+    assert ctx.selftest_division(1 << 32, seed=12345, exp_range=250) == 0
+    assert ctx.selftest_division(1 << 30, seed=777, exp_range=3) == 0
+    assert ctx.selftest_division(1 << 28, seed=99, exp_range=0) == 0
+
+
+@pytest.mark.parametrize("scale_coef,scale_diag", [(2.0 ** 140, 2.0 ** 140), (2.0 ** -140, 2.0 ** -140), (1.0, 2.0 ** -260), (1.0, 2.0 ** 260)])
+@pytest.mark.parametrize("precond", [abi.PRECOND_DIC, abi.PRECOND_DILU])
+def test_factor_sweep_exact_path_outside_fast_division_range(ctx, oracle, scale_coef, scale_diag, precond):
+    """The factor sweep's shared-reciprocal divisions are only used while exponents stay within 2^+-125 (coefficients) and
+    2^+-250 (diagonal entries); outside, the same sweep reruns with the plain FP64 operators.  Both ways the result is the
+    oracle's bit for bit: scaled coefficients trip the veto at gather time, a scaled diagonal (off-diagonals switched off) the
+    in-sweep range report."""
+    dims = (37, 19, 9)
+    lo, up = helpers.block_addressing_np(dims)
+    n = dims[0] * dims[1] * dims[2]
+    asym = precond == abi.PRECOND_DILU
+    diag, upper, lower, x, b = helpers.spd_coefficients(n, lo, up, seed=21, asym=asym)
+    if scale_coef == 1.0:
+        upper = upper * 0.0
+        lower = None if lower is None else lower * 0.0
+        diag = diag * scale_diag
+    else:
+        diag, upper = diag * scale_diag, upper * scale_coef
+        lower = None if lower is None else lower * scale_coef
+    s = lib.LduSolver(ctx, lo, up, n, block=dims)
+    for _ in range(2):          # the second call reuses the gathered coefficients (and their veto)
+        got = s.precondition(precond, b, diag, upper, lower)
+    ref = oracle_precond(oracle, n, lo, up, diag, upper, lower, precond, b)
+    # and an in-range matrix on the same solver afterwards goes back to the fast path with the right answer
+    d2, u2, l2, _, b2 = helpers.spd_coefficients(n, lo, up, seed=22, asym=asym)
+    got2 = s.precondition(precond, b2, d2, u2, l2)
+    ref2 = oracle_precond(oracle, n, lo, up, d2, u2, l2, precond, b2)
+    s.close()
+    assert np.array_equal(got, ref)
+    assert np.array_equal(got2, ref2)
