@@ -424,7 +424,10 @@ void Ldu::factor(int kind, const MatrixView& A)
                 a.ticket = waveFlags;
                 B200_CUDA(cudaMemsetAsync(waveFlags + 2, 0, sizeof(int), s));      // the veto of the fast factor sweep belongs to the off-diagonals
                 const int64_t rows = (int64_t)a.g.nTiles * a.g.nStepsPad;
-                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->smCount * 16));
+                int perSM = 8;
+                if (dilu) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_wave_gather<true>, 256, 0));
+                else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_wave_gather<false>, 256, 0));
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((rows + 7) / 8, (int64_t)ctx->smCount * std::max(perSM, 1)));
                 if (dilu) k_wave_gather<true><<<grid, 256, 0, s>>>(dims, a, A.upper, A.lower);
                 else k_wave_gather<false><<<grid, 256, 0, s>>>(dims, a, A.upper, A.lower);
                 B200_LAUNCH_CHECK();
