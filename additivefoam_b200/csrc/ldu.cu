@@ -383,6 +383,7 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         } while (0)
         if (cfg == 44) B200_W2(4, 4);
         else if (cfg == 83) B200_W2(8, 3);
+        else if (cfg == 82) B200_W2(8, 2);
         else if (cfg == 86) B200_W2(8, 6);
         else B200_W2(8, 4);
 #undef B200_W2

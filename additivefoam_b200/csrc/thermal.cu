@@ -508,11 +508,7 @@ void ThermalCase::step(b200_step_report* rep)
     ca.thermoTol = ctl.thermoTolerance; ca.Tmax = ctl.Tmax > 0 ? ctl.Tmax : kVGreat; ca.rDeltaT = rDeltaT; ca.rDeltaTEuler = rDeltaT;
     ca.rho = mat.rho; ca.Lf = mat.Lf;
     const size_t shm = 2 * (size_t)mat.nThermo * sizeof(double);
-    // a persistent grid of exactly the resident blocks (the corrector needs more registers than the 8 blocks/SM of cells_grid allow)
-    int perSM = 8;
-    if (explicitSolve) B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_corrector<true>, BLK, shm));
-    else B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_corrector<false>, BLK, shm));
-    const int grid = std::min(cells_grid(ctx, dims), ctx->smCount * std::max(perSM, 1));
+    const int grid = cells_grid(ctx, dims);
     SolveControls sc;
     sc.solver = ctl.solver; sc.precond = ctl.preconditioner; sc.tolerance = ctl.tolerance; sc.relTol = ctl.relTol;
     sc.minIter = ctl.minIter; sc.maxIter = ctl.maxIter;

@@ -293,8 +293,7 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
     B200_FOR_CELLS(d)
     {
         B200_CELL_INDEX(d)
-        // every operand of the cell up front: one DRAM round trip per item, not one before and one after the phase branches
-        const double x = a.T[c], y = a.alpha1[c], yOld = a.alpha1old[c], dg0 = a.diag0[c], sr0 = a.source0[c];
+        const double x = a.T[c], y = a.alpha1[c];
         double dF, t0;
         if (x < a.Tliq && x > a.Tsol) {
             int lo = 0;
@@ -315,10 +314,10 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         const double source1 = (g.V * (Acoef * a.Tmax)) * a.rDeltaT;
         const double diag2 = (g.V * dF) * s2;
         const double source2 = (g.V * (dF * t0)) * s2;
-        const double su = (a.rho * a.Lf) * (a.rDeltaTEuler * (y - yOld));
+        const double su = (a.rho * a.Lf) * (a.rDeltaTEuler * (y - a.alpha1old[c]));
         const double sourceR = source2 - g.V * su;
-        double dg = (dg0 + diag1) - diag2;
-        double sr = (sr0 + source1) - sourceR;
+        double dg = (a.diag0[c] + diag1) - diag2;
+        double sr = (a.source0[c] + source1) - sourceR;
         if (!EXPLICIT) {      // the explicit matrix has zero boundary coefficients
             const bool bnd = i == 0 || i == d.nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
             for (int q = 0; bnd && q < sd.nOrder; q++) {

@@ -128,17 +128,17 @@ def run_cpu(args, nz, steps, warmup, ranks):
 
 
 def ncu_traffic(group, n_local):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's kernel from the committed ncu --set full capture
-    (profiles/r1_top_kernels_ncu_full.csv, taken on the default 12.8 M-cell slab); None for other sizes or groups."""
-    tag = {"sweep_fwd": "<1,", "sweep_bwd": "<2,", "factor": "<0,", "amul": "k_amul_block<2>"}.get(group)
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's kernel from the committed ncu --set full capture of
+    this command (profiles/r1_top_kernels_ncu_full_<cells>.csv); None for sizes or groups that were not captured."""
+    tag = {"sweep_fwd": "k_wave2<1,", "sweep_bwd": "k_wave2<2,", "factor": "k_wave2<0,", "amul": "k_amul_block<2>"}.get(group)
     path = os.path.join(ROOT, "profiles", f"r1_top_kernels_ncu_full_{n_local}.csv")
     if tag is None or not os.path.exists(path):
         return None
     import csv
     rows = list(csv.reader(open(path)))
     hdr = rows[0]
-    vals = [float(r[hdr.index("dram_read_bytes")]) + float(r[hdr.index("dram_write_bytes")]) for r in rows[1:]
-            if r and tag in r[0] and ("k_wave" in r[0] or "k_amul" in r[0])]
+    vals = [float(r[hdr.index("dram_read_bytes")]) + float(r[hdr.index("dram_write_bytes")]) for r in rows[1:] if r and tag in r[0]]
+    vals = [v for v in vals if v > 1e6]       # the exact factor sweep behind the fast one returns at once: not a real launch
     return sum(vals) / len(vals) if vals else None
 
 
@@ -289,7 +289,10 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
                 "avg_launch_ms": per_launch_ms[dom], "launches": prof[dom][1], "share_of_kernel_time": shares.get(dom),
                 "group_shares": shares,
-                "group_GBps": {k: round(alg_bytes[k] / (per_launch_ms[k] * 1e-3) / 1e9, 1) for k in per_launch_ms if alg_bytes.get(k)}}
+                "group_GBps": {k: round(alg_bytes[k] / (per_launch_ms[k] * 1e-3) / 1e9, 1) for k in per_launch_ms if alg_bytes.get(k)},
+                "note": "achieved = SURVEY.md 8(d) algorithmic bytes (general LDU addressing: 72 B/cell for Amul and for each sweep) / "
+                        "measured launch time; the block path moves less (Amul 48, forward sweep 56, backward sweep 64 B/cell: no "
+                        "addressing arrays, see DESIGN.md section 5), so compare `traffic` / avg_launch_ms with the peak for the DRAM rate"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
