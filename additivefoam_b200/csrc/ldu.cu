@@ -117,7 +117,7 @@ Ldu::~Ldu()
     for (auto& p : stage) dev_free(p);
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace);
 }
 
 void Ldu::setBlock(int nx, int ny, int nz)
@@ -141,6 +141,10 @@ void Ldu::setBlock(int nx, int ny, int nz)
     useWave = !(e && std::string(e) == "coop");
     for (auto& w : work) dev_free(w);       // ghost padding changes
     dev_free(rD);
+    // the wave-order arrays, the tile order and the gathered coefficients belong to the block shape
+    for (auto& p : wave) dev_free(p);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace);
+    waveEpoch = -1; waveUpper = nullptr; waveLower = nullptr;
 }
 
 void Ldu::levels(int* levelOfCell, int* nLev)
@@ -330,6 +334,12 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.DG = wave[13];
     a.rA = rA; a.wA = wA;
     a.ticket = waveFlags; a.order = waveOrder; a.tilePartial = wavePartial; a.st = d_state;
+    a.trace = nullptr;
+    static const bool traceOn = [] { const char* e = std::getenv("B200_WAVE_TRACE"); return e && std::atoi(e) != 0; }();
+    if (traceOn) {
+        if (!waveTrace) waveTrace = dev_alloc<long long>((size_t)a.g.nTiles * 12);
+        a.trace = waveTrace;
+    }
     {
         // keep what the resident tiles have prefetched but not yet consumed well inside L2 (126 MB): about 32 MB in flight
         const int64_t resident = std::min<int64_t>(a.g.nTiles, (int64_t)ctx->smCount * 12);
@@ -396,6 +406,19 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         }
     }
     B200_LAUNCH_CHECK();
+    if (traceOn) {          // diagnostic: per-tile time stamps of this sweep, relative to the earliest, on stderr
+        std::vector<long long> h((size_t)a.g.nTiles * 12);
+        d2h(h.data(), waveTrace, h.size(), s);
+        ctx->sync();
+        long long t0 = h[11];
+        for (int t = 0; t < a.g.nTiles; t++) t0 = std::min(t0, h[12 * t + 11]);
+        std::fprintf(stderr, "WAVE_TRACE op %d nJ %d nK %d\n", op, a.g.nJ, a.g.nK);
+        for (int t = 0; t < a.g.nTiles; t++) {
+            std::fprintf(stderr, "WT %d %d", t % a.g.nJ, t / a.g.nJ);
+            for (int q = 0; q < 12; q++) std::fprintf(stderr, " %lld", h[12 * t + q] - t0);
+            std::fprintf(stderr, "\n");
+        }
+    }
     if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }
 }
 

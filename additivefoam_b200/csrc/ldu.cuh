@@ -121,6 +121,7 @@ public:
     double* wave[14] = {nullptr};    // A0 PX PY PZ QX QY QZ WF RF WB NX NY NZ DG
     int* waveFlags = nullptr;        // tile ticket
     int* waveOrder = nullptr;        // ticket -> tile
+    long long* waveTrace = nullptr;  // B200_WAVE_TRACE diagnostic
     double* wavePartial = nullptr;
     int64_t waveLen = 0;
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
