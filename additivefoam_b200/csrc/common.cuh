@@ -32,6 +32,28 @@ extern int64_t g_launches;     // kernels launched by this library (bench.py "gp
 inline void count_launch(int n = 1) { g_launches += n; }
 #define B200_LAUNCH_CHECK() do { ::b200::count_launch(); B200_CUDA(cudaGetLastError()); } while (0)
 
+// A read-only load that stays where it is written.  The compiler sinks ordinary loads next to (or into the branch of) their
+// first use, which turns `load a, b, c, ...; use a; use b; ...` into a chain of load -> wait -> use stages: one memory latency
+// per stage instead of one per cell.  A volatile asm is neither sunk nor reordered, so a block of ld_first() calls is issued
+// back to back.  Only for data no thread writes during the kernel (ld.global.nc).  Measured: it pays where a thread's loads come
+// from different arrays and nothing else hides the latency (the corrector of explicit steps 2.9 -> 1.8 ms, k_faces -8 %).  It
+// does NOT pay in the stencil kernels: Amul with all operands -- or one operand per cache line -- loaded first needs 48 instead
+// of 32 registers, 5 instead of 8 resident blocks, and went from 0.98 to 1.4-1.8 ms; that kernel lives on its 64 warps per SM.
+__device__ __forceinline__ double ld_first(const double* p)
+{
+    double v;
+    asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+// same, for data the loading thread itself overwrites later in the kernel (plain ld.global)
+__device__ __forceinline__ double ld_first_rw(const double* p)
+{
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // ---------------------------------------------------------------------------------------
 // Deterministic reductions.  Every reducing kernel runs with a fixed grid; each block
 // reduces with a fixed shuffle tree, writes its partial to `partials[slot][block]`, and

@@ -128,10 +128,12 @@ __global__ void __launch_bounds__(BLK) k_faces(BlockDims d, Geom g, const double
         const RowCtx r = row_ctx(d, row);
         int fzl, fyl, fxl, fx, fy, fz;
         cell_faces(d, r, i, fzl, fyl, fxl, fx, fy, fz);
-        const double rP = rKappa[c];
-        if (fx >= 0) { const double rN = rKappa[c + 1]; const double kf = 1.0 / (0.5 * (rP - rN) + rN); upper[fx] = EXPLICIT ? kf : 0.0 - g.dcx * (kf * g.sfx); }
-        if (fy >= 0) { const double rN = rKappa[c + nx]; const double kf = 1.0 / (0.5 * (rP - rN) + rN); upper[fy] = EXPLICIT ? kf : 0.0 - g.dcy * (kf * g.sfy); }
-        if (fz >= 0) { const double rN = rKappa[c + nxny]; const double kf = 1.0 / (0.5 * (rP - rN) + rN); upper[fz] = EXPLICIT ? kf : 0.0 - g.dcz * (kf * g.sfz); }
+        const double* rp = rKappa + c;
+        const double rP = ld_first(rp), rX = ld_first(fx >= 0 ? rp + 1 : rp), rY = ld_first(fy >= 0 ? rp + nx : rp),
+                     rZ = ld_first(fz >= 0 ? rp + nxny : rp);
+        if (fx >= 0) { const double kf = 1.0 / (0.5 * (rP - rX) + rX); upper[fx] = EXPLICIT ? kf : 0.0 - g.dcx * (kf * g.sfx); }
+        if (fy >= 0) { const double kf = 1.0 / (0.5 * (rP - rY) + rY); upper[fy] = EXPLICIT ? kf : 0.0 - g.dcy * (kf * g.sfy); }
+        if (fz >= 0) { const double kf = 1.0 / (0.5 * (rP - rZ) + rZ); upper[fz] = EXPLICIT ? kf : 0.0 - g.dcz * (kf * g.sfz); }
     }
 }
 
@@ -290,10 +292,7 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
     const double slope = 1e10;
     const double s2 = a.rDeltaT * a.rho * a.Lf;
     double mxRes = -1e300;
-    B200_FOR_CELLS(d)
-    {
-        B200_CELL_INDEX(d)
-        const double x = a.T[c], y = a.alpha1[c];
+    auto cell = [&](int i, int j, int k, int64_t c, double x, double y, double aold, double d0, double s0) {
         double dF, t0;
         if (x < a.Tliq && x > a.Tsol) {
             int lo = 0;
@@ -314,10 +313,10 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         const double source1 = (g.V * (Acoef * a.Tmax)) * a.rDeltaT;
         const double diag2 = (g.V * dF) * s2;
         const double source2 = (g.V * (dF * t0)) * s2;
-        const double su = (a.rho * a.Lf) * (a.rDeltaTEuler * (y - a.alpha1old[c]));
+        const double su = (a.rho * a.Lf) * (a.rDeltaTEuler * (y - aold));
         const double sourceR = source2 - g.V * su;
-        double dg = (a.diag0[c] + diag1) - diag2;
-        double sr = (a.source0[c] + source1) - sourceR;
+        double dg = (d0 + diag1) - diag2;
+        double sr = (s0 + source1) - sourceR;
         if (!EXPLICIT) {      // the explicit matrix has zero boundary coefficients
             const bool bnd = i == 0 || i == d.nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
             for (int q = 0; bnd && q < sd.nOrder; q++) {
@@ -336,6 +335,21 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
             a.alpha1[c] = an;
             mxRes = fmax(mxRes, fabs(an - y));
         }
+    };
+    // two items per trip: the loads of both are in flight before either is worked on (one cell per thread per trip left the
+    // kernel at half the memory parallelism the HBM needs)
+    const int segs = (d.nx + BLK - 1) / BLK, nItems = segs * d.ny * d.nz;
+    for (int itemA = blockIdx.x; itemA < nItems; itemA += 2 * gridDim.x) {
+        const int itemB = itemA + gridDim.x;
+        const int rowA = itemA / segs, iA = (itemA - rowA * segs) * BLK + threadIdx.x;
+        const int rowB = itemB / segs, iB = (itemB - rowB * segs) * BLK + threadIdx.x;
+        const bool okA = iA < d.nx, okB = itemB < nItems && iB < d.nx;
+        const int64_t cA = (int64_t)rowA * d.nx + iA, cB = (int64_t)rowB * d.nx + iB;
+        double xA = 0, yA = 0, oA = 0, dA = 0, sA = 0, xB = 0, yB = 0, oB = 0, dB = 0, sB = 0;
+        if (okA) { xA = ld_first_rw(a.T + cA); yA = ld_first_rw(a.alpha1 + cA); oA = ld_first(a.alpha1old + cA); dA = ld_first(a.diag0 + cA); sA = ld_first(a.source0 + cA); }
+        if (okB) { xB = ld_first_rw(a.T + cB); yB = ld_first_rw(a.alpha1 + cB); oB = ld_first(a.alpha1old + cB); dB = ld_first(a.diag0 + cB); sB = ld_first(a.source0 + cB); }
+        if (okA) { const int k = rowA / d.ny; cell(iA, rowA - k * d.ny, k, cA, xA, yA, oA, dA, sA); }
+        if (okB) { const int k = rowB / d.ny; cell(iB, rowB - k * d.ny, k, cB, xB, yB, oB, dB, sB); }
     }
     if (EXPLICIT) {
         __shared__ double smem[32];
