@@ -137,7 +137,7 @@ ShapeParams heatSourceModel::shapeParams() const
 // =====================================================================================
 // Device: per-cell Riemann sum of the beam shape (heatSourceModel.C:287-356)
 // =====================================================================================
-__device__ __forceinline__ double shape_weight(const ShapeParams& sp, double dxv, double dyv, double dzv)
+__host__ __device__ __forceinline__ double shape_weight(const ShapeParams& sp, double dxv, double dyv, double dzv)
 {
     if (sp.model == B200_SUPER_GAUSSIAN) {                     // superGaussian.C:62-70
         const double a = pow(2.0, 1.0 / sp.k);
@@ -160,6 +160,12 @@ __device__ __forceinline__ double shape_weight(const ShapeParams& sp, double dxv
     const double f = exp(-2.0 * (ux * ux + uy * uy));
     const double s = exp(-3.0 * pow(fabs(fabs(dzv) / sp.dims[2]), sp.k));
     return f * s;
+}
+
+// heatSourceModel::weight() on the host (b200_beam_shape_weight): the same function the kernel calls
+double heatSourceModel::weight(const double d[3]) const
+{
+    return shape_weight(shapeParams(), d[0], d[1], d[2]);
 }
 
 // One warp per cell of the index box; lanes stride over the sample points.

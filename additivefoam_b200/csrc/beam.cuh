@@ -57,6 +57,7 @@ public:
     heatSourceModel(const b200_beam& b, double startTime, double endTimeOfRun);
     double eta(double aspectRatio) const;                 // absorptionModel::eta
     double V0();                                          // shape normalisation (mutates k for projectedGaussian)
+    double weight(const double d[3]) const;               // heatSourceModel::weight for a component-wise distance
     ShapeParams shapeParams() const;
     movingBeam beam;
     b200_beam spec{};

@@ -261,6 +261,44 @@ int b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam* 
     B200_CATCH
 }
 
+static heatSourceModel host_model(const b200_beam* beam, const double dimensions[3])
+{
+    B200_CHECK(beam != nullptr && dimensions != nullptr, "null beam or dimensions");
+    B200_CHECK(beam->heatSourceModel >= B200_SUPER_GAUSSIAN && beam->heatSourceModel <= B200_PROJECTED_GAUSSIAN, "unknown heatSourceModel");
+    b200_beam b = *beam;
+    b.nSegments = 0; b.path = nullptr;                 // the shape does not depend on the path
+    heatSourceModel m(b, 0.0, 0.0);
+    for (int q = 0; q < 3; q++) m.dimensions[q] = dimensions[q];
+    return m;
+}
+int b200_beam_shape_v0(const b200_beam* beam, const double dimensions[3], double* V0, double* kResolved)
+{
+    B200_TRY
+    heatSourceModel m = host_model(beam, dimensions);
+    const double v = m.V0();
+    if (V0) *V0 = v;
+    if (kResolved) *kResolved = m.k;
+    B200_CATCH
+}
+int b200_beam_shape_weight(const b200_beam* beam, const double dimensions[3], const double d[3], double* weight)
+{
+    B200_TRY
+    B200_CHECK(d != nullptr && weight != nullptr, "null argument");
+    heatSourceModel m = host_model(beam, dimensions);
+    m.V0();                                            // heatSourceModel.C:260: V0() precedes every weight()
+    *weight = m.weight(d);
+    B200_CATCH
+}
+int b200_beam_absorption_eta(const b200_beam* beam, double aspectRatio, double* eta)
+{
+    B200_TRY
+    B200_CHECK(beam != nullptr && eta != nullptr, "null argument");
+    b200_beam b = *beam;
+    b.nSegments = 0; b.path = nullptr;
+    *eta = heatSourceModel(b, 0.0, 0.0).eta(aspectRatio);
+    B200_CATCH
+}
+
 int b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out)
 {
     B200_TRY

@@ -27,7 +27,7 @@ SYMBOLS = [
     "b200_ctx_peer_export", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
-    "b200_beam_qdot", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
+    "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
     "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse",
@@ -95,6 +95,9 @@ def load():
     L.b200_ldu_precondition.argtypes = [vp, C.c_int32, dp, dp, dp, dp, dp]
     L.b200_ldu_levels.argtypes = [vp, ip, ip]
     L.b200_beam_qdot.argtypes = [vp, C.POINTER(abi.BlockMesh), C.POINTER(abi.Beam), dp, dp, C.c_double, dp, dp, dp, dp]
+    L.b200_beam_shape_v0.argtypes = [C.POINTER(abi.Beam), dp, dp, dp]
+    L.b200_beam_shape_weight.argtypes = [C.POINTER(abi.Beam), dp, dp, dp]
+    L.b200_beam_absorption_eta.argtypes = [C.POINTER(abi.Beam), C.c_double, dp]
     L.b200_case_create.argtypes = [vp, C.POINTER(abi.CaseDesc), C.POINTER(vp)]
     L.b200_case_destroy.argtypes = [vp]
     L.b200_case_running.argtypes = [vp]
@@ -332,6 +335,31 @@ class Case:
         if self.h:
             self.L.b200_case_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def beam_shape_V0(beam, dimensions):
+    """heatSourceModel::V0() for the current dimensions (host only); returns (V0, k) -- k is the shape exponent, which
+    projectedGaussian re-derives from the depth (projectedGaussian.C:96-106)."""
+    b, d = cases.make_beam(beam), _f64(dimensions)
+    v, k = C.c_double(), C.c_double()
+    _check(load().b200_beam_shape_v0(C.byref(b), _P(d), C.cast(C.byref(v), dp), C.cast(C.byref(k), dp)))
+    return v.value, k.value
+
+
+def beam_shape_weight(beam, dimensions, distance):
+    """heatSourceModel::weight(d) for a component-wise distance from the beam centre (host only)."""
+    b, d, x = cases.make_beam(beam), _f64(dimensions), _f64(distance)
+    w = C.c_double()
+    _check(load().b200_beam_shape_weight(C.byref(b), _P(d), _P(x), C.cast(C.byref(w), dp)))
+    return w.value
+
+
+def beam_absorption_eta(beam, aspect_ratio):
+    """absorptionModel::eta(aspectRatio) (host only)."""
+    b = cases.make_beam(beam)
+    e = C.c_double()
+    _check(load().b200_beam_absorption_eta(C.byref(b), aspect_ratio, C.cast(C.byref(e), dp)))
+    return e.value
 
 
 def scan_path_parse(text, max_segments=4096):

@@ -234,6 +234,15 @@ int  b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam*
                     const double position[3], const double dimensions[3], double power,
                     double* qDot, double* sumWeights, double* volumeUsed, double* absorbedPower);
 
+/* The two pure virtuals of heatSourceModel (heatSourceModel.H:197-200) and absorptionModel::eta, evaluated by the library's host
+ * mirror of the beam models (no device, no context): V0() for the given current dimensions -- for projectedGaussian it also
+ * resolves the shape exponent k from the depth, projectedGaussian.C:96-106, returned in kResolved (may be NULL) -- and weight(d)
+ * for a component-wise distance d from the beam centre.  The OpenFOAM-side heat-source shims forward their virtuals to
+ * these, so the shape formulas live in one place. */
+int  b200_beam_shape_v0(const b200_beam* beam, const double dimensions[3], double* V0, double* kResolved);
+int  b200_beam_shape_weight(const b200_beam* beam, const double dimensions[3], const double d[3], double* weight);
+int  b200_beam_absorption_eta(const b200_beam* beam, double aspectRatio, double* eta);
+
 /* ---- The GPU-resident thermal step (everything in SURVEY section 3.2 items 1,3,4,6,8). */
 int  b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out);
 int  b200_case_destroy(b200_case* c);

@@ -64,3 +64,32 @@ def test_case_descriptions_build():
     pbf = cases.multi_layer_pbf((100, 50, 40))
     assert pbf["controls"]["Tmax"] == 3300.0 and pbf["powderZMin"] == -40e-6
     assert len(cases.multi_beam((100, 25, 20))["beams"]) == 4
+
+
+def test_host_shape_functions_match_oracle_and_known_answers(oracle):
+    """b200_beam_shape_v0 / _weight / b200_beam_absorption_eta (what the OpenFOAM heat-source shims forward their pure virtuals
+    to) are host code: checked here against the oracle's restatement and the hand-derived values of tests/golden."""
+    import ctypes as C
+    import json
+    import oracle_lib as ol
+    ka = json.load(open(os.path.join(ROOT, "tests", "golden", "known_answers.json")))
+    path = [[1, 0, 0, 0, 100.0, 0.0], [0, 1e-3, 0, 0, 100.0, 0.8]]
+    beams = [cases.super_gaussian_beam(path), cases.modified_super_gaussian_beam(path), cases.projected_gaussian_beam(path)]
+    v0, _ = lib.beam_shape_V0(beams[0], (85e-6, 85e-6, 30e-6))
+    assert v0 == pytest.approx(ka["superGaussian_V0_k2_85_85_30um"], rel=1e-14)
+    v0, _ = lib.beam_shape_V0(beams[1], (40e-6, 40e-6, 30e-6))
+    assert v0 == pytest.approx(ka["modifiedSuperGaussian_V0_k7.95_m2.72_40_40_30um"], rel=1e-13)
+    assert lib.beam_absorption_eta(beams[1], 0.75) == ka["kelly_cone_eta_aspect_0.75"]
+    assert lib.beam_absorption_eta(beams[1], 2.0) == pytest.approx(ka["kelly_cone_eta_aspect_2"], rel=1e-14)
+    rng = np.random.default_rng(5)
+    for b in beams:
+        ob = cases.make_beam(b)
+        for depth in (30e-6, 55e-6, 170e-6):          # transient beams change dimensions.z (heatSourceModel.C:207-213)
+            dims = np.array([b["dimensions"][0], b["dimensions"][1], depth])
+            assert lib.beam_shape_V0(b, dims)[0] == pytest.approx(oracle.afo_shape_V0(C.byref(ob), ol.P(dims)), rel=1e-14)
+            for _ in range(40):
+                d = np.abs(rng.normal(0, 1, 3)) * dims * 0.8
+                got, ref = lib.beam_shape_weight(b, dims, d), oracle.afo_shape_weight(C.byref(ob), ol.P(dims), ol.P(d))
+                assert got == pytest.approx(ref, rel=1e-13, abs=1e-300)
+        for aspect in (0.3, 1.0, 1.0000001, 2.0, 7.5):
+            assert lib.beam_absorption_eta(b, aspect) == pytest.approx(oracle.afo_absorption_eta(C.byref(ob), aspect), rel=1e-14)

@@ -1,4 +1,4 @@
-"""The OpenFOAM-side lduMatrix::solver shim (openfoam/bPCG) must at least parse against declarations that mirror the
+"""The OpenFOAM-side shims (openfoam/bPCG: lduMatrix::solver; openfoam/b200HeatSource: heatSourceModel) must at least parse against declarations that mirror the
 upstream interface (OpenFOAM-10 is not installable here) and call only functions the C header declares."""
 import os
 import re
@@ -14,10 +14,25 @@ def test_bpcg_shim_parses_against_stub_headers():
     assert out.returncode == 0, out.stderr[-3000:]
 
 
+def test_heat_source_shim_parses_against_stub_headers():
+    cmd = ["g++", "-std=c++14", "-fsyntax-only", "-I" + os.path.join(ROOT, "openfoam", "stubs"),
+           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "openfoam", "b200HeatSource", "b200HeatSources.C")]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr[-3000:]
+
+
+def test_heat_source_shim_registers_the_three_shapes():
+    src = open(os.path.join(ROOT, "openfoam", "b200HeatSource", "b200HeatSources.C")).read()
+    for cls, shape in (("b200SuperGaussian", "B200_SUPER_GAUSSIAN"), ("b200ModifiedSuperGaussian", "B200_MODIFIED_SUPER_GAUSSIAN"),
+                       ("b200ProjectedGaussian", "B200_PROJECTED_GAUSSIAN")):
+        assert f"addToRunTimeSelectionTable(heatSourceModel, {cls}, dictionary)" in src
+        assert f"B200_DEFINE_HEAT_SOURCE({cls}, {shape})" in src
+
+
 def test_shims_call_only_declared_entry_points():
     hdr = open(os.path.join(ROOT, "include", "additivefoam_b200.h")).read()
     declared = set(re.findall(r"\b(b200_[a-z_0-9]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
-    for rel in ("bPCG/bPCG.C", "b200HeatSource/b200SuperGaussian.C"):
+    for rel in ("bPCG/bPCG.C", "b200HeatSource/b200HeatSources.C"):
         src = open(os.path.join(ROOT, "openfoam", rel)).read()
         used = set(re.findall(r"\b(b200_[a-z_0-9]+)\s*\(", src))
         assert used and used <= declared, used - declared
