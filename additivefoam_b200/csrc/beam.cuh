@@ -12,6 +12,7 @@
 #include "../../include/additivefoam_b200.h"
 #include "common.cuh"
 #include <vector>
+#include <string>
 #include <cmath>
 
 namespace b200 {
@@ -65,5 +66,9 @@ public:
     double k = 0;
     bool transient = false;
 };
+
+// applications/utilities/createScanPath: file text of one rotation (scanpath.cu)
+std::string create_scan_path(const double minPoint[2], const double maxPoint[2], double hatch, double rotationDeg, double power,
+                             double speed, double dwellTime, bool biDirection);
 
 } // namespace b200

@@ -4,6 +4,8 @@
 #include "ldu.cuh"
 #include "thermal.cuh"
 #include <cstring>
+#include <algorithm>
+#include <string>
 #include <sstream>
 
 using namespace b200;
@@ -372,6 +374,21 @@ int b200_case_kernel_launches(b200_case*, int64_t* launches)
 {
     *launches = g_launches;
     return 0;
+}
+
+int b200_create_scan_path(const double minPoint[2], const double maxPoint[2], double hatch, double rotationDeg, double power,
+                          double speed, double dwellTime, int32_t biDirection, char* text, int64_t capacity, int64_t* length)
+{
+    B200_TRY
+    B200_CHECK(minPoint != nullptr && maxPoint != nullptr && length != nullptr, "null argument");
+    const std::string s = create_scan_path(minPoint, maxPoint, hatch, rotationDeg, power, speed, dwellTime, biDirection != 0);
+    *length = (int64_t)s.size();
+    if (text != nullptr && capacity > 0) {
+        const size_t nCopy = std::min<size_t>(s.size(), (size_t)capacity);
+        std::memcpy(text, s.data(), nCopy);
+        if (nCopy < (size_t)capacity) text[nCopy] = 0;
+    }
+    B200_CATCH
 }
 
 int b200_scan_path_parse(const char* text, double* out, int32_t maxSegments)

@@ -1,5 +1,6 @@
 #include "ldu_kernels.cuh"
 #include "wave_kernels.cuh"
+#include "flow_kernels.cuh"
 #include <cstdlib>
 #include <set>
 #include "ctx.cuh"
@@ -69,6 +70,10 @@ Ldu::Ldu(Ctx* c, int nCells_, int nFaces_, const int* lower, const int* upper, i
         for (int cI = 0; cI < nCells; cI++) lvlCells[pos[level[cI]]++] = cI;
     }
     h_level = level;
+    {
+        const char* e = std::getenv("B200_SWEEP");          // "coop": one cooperative launch with a grid barrier per level
+        useFlow = !(e && std::string(e) == "coop");
+    }
     cudaStream_t s = ctx->stream;
     d_lower = dev_alloc<int>(nFaces); d_upper = dev_alloc<int>(nFaces);
     d_rowStart = dev_alloc<int>(nCells + 1); d_rowMid = dev_alloc<int>(nCells);
@@ -118,6 +123,7 @@ Ldu::~Ldu()
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
     dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace);
+    dev_free(flowF); dev_free(flowPartial); dev_free(flowTicket);
 }
 
 void Ldu::setBlock(int nx, int ny, int nz)
@@ -462,6 +468,13 @@ void Ldu::factor(int kind, const MatrixView& A)
         } else if (isBlock) {
             if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
             else coop_launch(ctx, k_sweep_block<0, false, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
+        } else if (useFlow) {
+            // raw recurrence values into a sentinel-filled rD; the forward scratch is reset here too, once per solve
+            const int grid = std::max(1, std::min(redBlocks, (nCells + BLK - 1) / BLK));
+            if (!flowF) flowF = dev_alloc<double>((size_t)std::max(nCells, 1));
+            k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, rd, st); B200_LAUNCH_CHECK();
+            k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowF, st); B200_LAUNCH_CHECK();
+            flowSweep(0, dilu, false, A, nullptr, nullptr, nullptr);
         } else {
             const int* ls = d_lvlStart;
             if (dilu) coop_launch(ctx, k_sweep_general<0, true, false>, (int64_t)maxLevelSize, nLevels, ls, (const int*)d_lvlCells, (const int*)d_rowStart, (const int*)d_rowMid, (const int*)d_rowCol, (const int*)d_rowFace, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
@@ -469,6 +482,42 @@ void Ldu::factor(int kind, const MatrixView& A)
         }
     }
     k_reciprocal<<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rD + ghost, st); B200_LAUNCH_CHECK();
+}
+
+// what: 0 factor recurrence (rD sentinel-filled by the caller), 1 forward, 2 backward (+ dot into S_RHO)
+void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec)
+{
+    cudaStream_t s = ctx->stream;
+    const int nChunks = (nCells + 31) / 32;              // one per warp ticket
+    if (nChunks == 0) return;
+    if (!flowTicket) { flowTicket = dev_alloc<int>(1); flowPartial = dev_alloc<double>((size_t)nChunks); }
+    FlowArgs a;
+    a.n = nCells; a.lvlCells = d_lvlCells; a.rowStart = d_rowStart; a.rowMid = d_rowMid; a.rowCol = d_rowCol; a.rowFace = d_rowFace;
+    a.diag = A.diag; a.upper = A.upper; a.lower = A.lower; a.rD = rD + ghost; a.rA = rA; a.F = flowF; a.wA = wA; a.dotVec = dotVec;
+    a.chunkPartial = flowPartial; a.ticket = flowTicket; a.st = d_state;
+    static int perSM = 0;
+    if (!perSM) {
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sweep_flow<2, false, true>, BLK, 0));
+        perSM = std::max(perSM, 1);
+    }
+    static const int envBlocks = [] { const char* e = std::getenv("B200_FLOW_BLOCKS"); return e ? std::atoi(e) : 0; }();
+    static const int envSleep = [] { const char* e = std::getenv("B200_FLOW_SLEEP"); return e ? std::atoi(e) : 0; }();
+    a.sleepNs = envSleep;
+    // few warps in flight: the ones far ahead of the front only poll, and their polls are L2 traffic the front has to queue behind
+    const int grid = std::min((nChunks + BLK / 32 - 1) / (BLK / 32), ctx->smCount * std::min(envBlocks > 0 ? envBlocks : 2, perSM));
+    B200_CUDA(cudaMemsetAsync(flowTicket, 0, sizeof(int), s));
+    if (what == 0) {
+        if (dilu) k_sweep_flow<0, true, false><<<grid, BLK, 0, s>>>(a);
+        else k_sweep_flow<0, false, false><<<grid, BLK, 0, s>>>(a);
+    } else if (what == 1) {
+        if (dilu) k_sweep_flow<1, true, false><<<grid, BLK, 0, s>>>(a);
+        else k_sweep_flow<1, false, false><<<grid, BLK, 0, s>>>(a);
+    } else {
+        if (dot) k_sweep_flow<2, false, true><<<grid, BLK, 0, s>>>(a);
+        else k_sweep_flow<2, false, false><<<grid, BLK, 0, s>>>(a);
+    }
+    B200_LAUNCH_CHECK();
+    if (what == 2 && dot) { k_sum<<<red_blocks_for(nChunks), BLK, 0, s>>>((int64_t)nChunks, flowPartial, red, (int)S_RHO, d_state); B200_LAUNCH_CHECK(); }
 }
 
 // wA = M^-1 rA, optionally with sum(wA . dotVec) into slot S_RHO
@@ -491,6 +540,9 @@ void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* 
         else { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
         if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, true>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st); }
         else { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
+    } else if (useFlow) {
+        { ProfScope ps_(ctx, PC_SWEEP_FWD); flowSweep(1, dilu, false, A, rA, wA, nullptr); }
+        { ProfScope ps_(ctx, PC_SWEEP_BWD); flowSweep(2, dilu, doDot != 0, A, rA, wA, dotVec); }
     } else {
         const int* ls = d_lvlStart; const int* lc = d_lvlCells; const int* rs = d_rowStart; const int* rm = d_rowMid;
         const int* rc = d_rowCol; const int* rf = d_rowFace;

@@ -125,6 +125,12 @@ public:
     double* wavePartial = nullptr;
     int64_t waveLen = 0;
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
+    // barrier-free level-ordered sweeps over general addressing (flow_kernels.cuh)
+    bool useFlow = true;
+    double* flowF = nullptr;         // forward result, all sentinel between applications
+    double* flowPartial = nullptr;   // per-chunk sums of the fused dot product
+    int* flowTicket = nullptr;
+    void flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec);
     void ensureWave(bool dilu);
     void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio);
     int waveVecGrid();

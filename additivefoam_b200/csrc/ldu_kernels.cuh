@@ -341,8 +341,9 @@ __global__ void __launch_bounds__(BLK) k_dot(int64_t n, const double* __restrict
     double v[1] = {acc}; const int ops[1] = {0};
     grid_reduce<1>(v, ops, red, slot, smem);
 }
-__global__ void __launch_bounds__(BLK) k_sum(int64_t n, const double* __restrict__ a, RedWork red, int slot)
+__global__ void __launch_bounds__(BLK) k_sum(int64_t n, const double* __restrict__ a, RedWork red, int slot, const SolveState* st = nullptr)
 {
+    if (solve_done(st)) return;
     double acc = 0;
     for (int64_t c = blockIdx.x * (int64_t)BLK + threadIdx.x; c < n; c += (int64_t)gridDim.x * BLK) acc += a[c];
     __shared__ double smem[32];

@@ -17,7 +17,7 @@ import numpy as np
 from . import abi, cases
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libadditivefoam_b200.so")
+SO_PATH = os.environ.get("B200_LIBRARY") or os.path.join(_HERE, "libadditivefoam_b200.so")
 
 dp, ip = abi.c_double_p, abi.c_int32_p
 
@@ -30,7 +30,7 @@ SYMBOLS = [
     "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
     "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
-    "b200_scan_path_parse",
+    "b200_scan_path_parse", "b200_create_scan_path",
 ]
 
 _lib = None
@@ -111,6 +111,8 @@ def load():
     L.b200_selftest_division.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
     L.b200_case_kernel_launches.argtypes = [vp, C.POINTER(C.c_int64)]
     L.b200_scan_path_parse.argtypes = [C.c_char_p, dp, C.c_int32]
+    L.b200_create_scan_path.argtypes = [dp, dp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32,
+                                        C.c_char_p, C.c_int64, C.POINTER(C.c_int64)]
     _lib = L
     return L
 
@@ -360,6 +362,24 @@ def beam_absorption_eta(beam, aspect_ratio):
     e = C.c_double()
     _check(load().b200_beam_absorption_eta(C.byref(b), aspect_ratio, C.cast(C.byref(e), dp)))
     return e.value
+
+
+def create_scan_path(min_point, max_point, hatch, angle, n_rotations, power, speed, dwell_time, bi_direction=True):
+    """applications/utilities/createScanPath: the texts of constant/scanPath_0 .. scanPath_<nRotations-1>
+    (createScanPath.C:74-101: file i is turned by i accumulated additions of ``angle`` degrees)."""
+    L = load()
+    lo, hi = _f64(min_point), _f64(max_point)
+    out, rotation = [], 0.0
+    for _ in range(n_rotations):
+        n = C.c_int64()
+        _check(L.b200_create_scan_path(_P(lo), _P(hi), hatch, rotation, power, speed, dwell_time, int(bool(bi_direction)), None, 0,
+                                       C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        _check(L.b200_create_scan_path(_P(lo), _P(hi), hatch, rotation, power, speed, dwell_time, int(bool(bi_direction)), buf,
+                                       n.value + 1, C.byref(n)))
+        out.append(buf.value.decode())
+        rotation += angle
+    return out
 
 
 def scan_path_parse(text, max_segments=4096):

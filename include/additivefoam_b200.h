@@ -282,6 +282,16 @@ int  b200_case_kernel_launches(b200_case* c, int64_t* launches);
  * skipped, blank lines skipped).  Returns the number of segments, or -1. */
 int  b200_scan_path_parse(const char* text, double* out, int32_t maxSegments);
 
+/* Raster scan path of one rotation angle as file text -- what applications/utilities/createScanPath writes into
+ * constant/scanPath_<i> (createScanPath.C:74-101 loops over nRotations with rotation += angle; createFields.H:265-392 makes
+ * and writes the lines): hatch lines `hatch` apart about the centre of the box [minPoint, maxPoint], turned by rotationDeg
+ * about that centre, cropped to the box, odd lines reversed when biDirection, each preceded by a point-source row carrying
+ * dwellTime (none before the first).  Writes at most `capacity` bytes (NUL-terminated when it fits) and the full length
+ * (without NUL) to *length; returns nonzero on bad arguments.  Byte-identical to the reference's writer. */
+int  b200_create_scan_path(const double minPoint[2], const double maxPoint[2], double hatch, double rotationDeg,
+                           double power, double speed, double dwellTime, int32_t biDirection,
+                           char* text, int64_t capacity, int64_t* length);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,6 @@
 """Micro-benchmark / profiling driver for the block LDU kernels (Amul, DIC sweeps, PCG) on a seeded SPD matrix
-(SURVEY.md 8d micro-bench).  Usage: python tools/perf_ldu.py NX NY NZ [reps] [what: precond|amul|solve]"""
+(SURVEY.md 8d micro-bench).  Usage: python tools/perf_ldu.py NX NY NZ [reps] [what: precond|amul|solve] [block|general]
+`general` hands the same matrix over without the block declaration: the arbitrary-addressing kernels a decomposed OpenFOAM case gets."""
 import ctypes as C
 import os
 import sys
@@ -16,6 +17,7 @@ from additivefoam_b200 import abi, lib  # noqa: E402
 nx, ny, nz = (int(v) for v in sys.argv[1:4])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 5
 what = sys.argv[5] if len(sys.argv) > 5 else "precond"
+addressing = sys.argv[6] if len(sys.argv) > 6 else "block"
 O = ol.load()
 n, nf, lo, up = ol.block_addressing(O, (nx, ny, nz))
 rng = np.random.default_rng(1234)
@@ -26,7 +28,7 @@ np.subtract.at(diag, up, upper)
 b = rng.uniform(-1, 1, n)
 x = rng.uniform(-1, 1, n)
 ctx = lib.Context(0)
-s = lib.LduSolver(ctx, lo, up, n, block=(nx, ny, nz))
+s = lib.LduSolver(ctx, lo, up, n, block=(nx, ny, nz) if addressing == "block" else None)
 for r in range(reps + 1):
     if r == 1:
         ctx.profile_enable(True)      # the first call allocates; time from the second on
