@@ -14,8 +14,8 @@
 //   * inside a warp a cell may depend on a cell of another lane (small levels).  Lanes therefore never spin on their
 //     own: the warp loops `while (!all done) { every pending lane tries to advance }`, which makes progress whenever
 //     any lane can;
-//   * forward writes F (scratch) and re-arms the caller's result array, backward reads F, re-arms it and writes the
-//     result: both arrays are all-sentinel again when the next application starts.
+//   * forward writes F and re-arms B, backward reads F, re-arms it and writes B (polled by the neighbours) plus the
+//     caller's result: F and B are all-sentinel again when the next application starts.
 // The dot product fused into the backward sweep is summed per chunk (fixed tree) and then over the chunks by a fixed grid
 // (k_sum), so it does not depend on which warp got which ticket.
 #pragma once
@@ -29,29 +29,56 @@ __device__ __forceinline__ void st_relaxed_f64(double* p, double v)
     asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// Everything the sweeps touch apart from the caller's vectors lives in POSITION order (position = index in the level-ordered
+// cell list): the dependency tables (neighbour positions, in the order the reference consumes them), the coefficients
+// gathered next to them once per solve, rD, the forward result F and the backward result B the neighbours poll.  A warp's 32
+// positions therefore read and write whole lines, and the polled entries -- positions in the neighbouring level -- are close
+// to each other.  Only rA[cell], the result wA[cell] and the dot-product operand are accessed through the cell number.
 struct FlowArgs {
     int n;                                   // cells
-    const int *lvlCells, *rowStart, *rowMid, *rowCol, *rowFace;
-    const double *diag, *upper, *lower;
-    double* rD;                              // WHAT 0: raw recurrence values (sentinel-filled before); else the reciprocals
-    const double* rA;
-    double* F;                               // forward result (scratch, all sentinel between applications)
-    double* wA;                              // result
-    const double* dotVec;
+    const int* perm;                         // position -> cell
+    const int *fStart, *fPos;                // lower-side faces of each position: [fStart[p], fStart[p+1]) neighbour positions, ascending face order
+    const int *bStart, *bPos;                // owned faces: neighbour positions, DESCENDING face order (as the backward sweep consumes them)
+    const double *coefF, *coefB;             // coefficients next to fPos / bPos: (DILU ? lower : upper)[face] / upper[face]
+    const double* numF;                      // factor numerators next to fPos: upper*upper (DIC) or upper*lower (DILU)
+    const double* diag;                      // natural order (factor)
+    double* rD;                              // position order: raw recurrence values during the factor sweep, reciprocals afterwards
+    const double* rA;                        // natural order
+    double* F;                               // position order, all sentinel between applications
+    double* B;                               // position order, all sentinel between applications' backward sweeps
+    double* wA;                              // natural order result
+    const double* dotVec;                    // natural order
     double* chunkPartial;                    // [nChunks] (DOT)
     int* ticket;
     int sleepNs;                             // back-off between two unsuccessful polls of a warp
     const SolveState* st;
 };
 
-// WHAT: 0 = calcReciprocalD recurrence (raw values; k_reciprocal follows), 1 = forward substitution, 2 = backward substitution
-// A warp takes 32 consecutive positions per ticket.  Everything a cell needs apart from its neighbours' results -- the
-// neighbour ids and the coefficients, FG faces at a time -- is in registers before the first poll, and the pending
-// neighbours of a group are polled with independent loads, so that once they are there a cell costs one L2 round trip
-// (polling them one after the other, each behind its own rowFace -> upper chain, cost ~4 us per level instead of ~1).
+// once per solve: coefficients from LDU face order into the position-ordered dependency tables
+template <bool DILU>
+__global__ void __launch_bounds__(BLK) k_flow_gather(int nFaces, const int* __restrict__ fFace, const int* __restrict__ bFace,
+                                                     const double* __restrict__ upper, const double* __restrict__ lower,
+                                                     double* __restrict__ coefF, double* __restrict__ coefB, double* __restrict__ numF,
+                                                     const SolveState* st)
+{
+    if (solve_done(st)) return;
+    for (int e = blockIdx.x * BLK + threadIdx.x; e < nFaces; e += gridDim.x * BLK) {
+        const int f = fFace[e];
+        const double u = upper[f];
+        coefF[e] = DILU ? lower[f] : u;
+        numF[e] = DILU ? u * lower[f] : u * u;
+        coefB[e] = upper[bFace[e]];
+    }
+}
+
+// WHAT: 0 = calcReciprocalD recurrence (raw values; the reciprocal pass follows), 1 = forward substitution, 2 = backward substitution
+// A warp takes 32 consecutive positions per ticket.  Neighbour positions and coefficients are in registers before the first
+// poll (FG faces at a time) and the pending neighbours of a group are polled with independent loads, so that once they are
+// there a cell costs one L2 round trip (polling them one after the other, each behind its own index -> coefficient chain,
+// cost ~4 us per level instead of ~1).
 constexpr int FG = 4;
 
-template <int WHAT, bool DILU, bool DOT>
+template <int WHAT, bool DOT>
 __global__ void __launch_bounds__(BLK) k_sweep_flow(FlowArgs a)
 {
     if (solve_done(a.st)) return;
@@ -59,24 +86,29 @@ __global__ void __launch_bounds__(BLK) k_sweep_flow(FlowArgs a)
     const int nChunks = (a.n + 31) / 32;
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    double* out = WHAT == 0 ? a.rD : WHAT == 1 ? a.F : a.wA;
+    double* out = WHAT == 0 ? a.rD : WHAT == 1 ? a.F : a.B;
+    const int* start = WHAT == 2 ? a.bStart : a.fStart;
+    const int* nbr = WHAT == 2 ? a.bPos : a.fPos;
+    const double* cf = WHAT == 0 ? a.numF : WHAT == 1 ? a.coefF : a.coefB;
     for (;;) {
         int chunk = 0;
         if (lane == 0) chunk = atomicAdd(a.ticket, 1);
         chunk = __shfl_sync(FULL, chunk, 0);
         if (chunk >= nChunks) break;
-        const int pos = chunk * 32 + lane;
-        const bool act = pos < a.n;
+        const int q0 = chunk * 32 + lane;
+        const bool act = q0 < a.n;
         // forward sweeps walk the level order upwards, the backward sweep downwards
-        const int c = act ? a.lvlCells[WHAT == 2 ? a.n - 1 - pos : pos] : 0;
-        int e = 0, left = 0;                 // next face of the row (ascending, or descending for WHAT 2) and how many remain
+        const int pos = act ? (WHAT == 2 ? a.n - 1 - q0 : q0) : 0;
+        const int c = act ? a.perm[pos] : 0;
+        int e = 0, left = 0;                 // next entry of the position's dependency list and how many remain
         double w = 0, r = 0;
         if (act) {
-            if (WHAT == 0) { w = a.diag[c]; e = a.rowStart[c]; left = a.rowMid[c] - e; }
-            else if (WHAT == 1) { r = a.rD[c]; w = r * a.rA[c]; e = a.rowStart[c]; left = a.rowMid[c] - e; a.wA[c] = sent; }
-            else { r = a.rD[c]; w = a.F[c]; a.F[c] = sent; e = a.rowStart[c + 1] - 1; left = e + 1 - a.rowMid[c]; }
+            e = start[pos]; left = start[pos + 1] - e;
+            if (WHAT == 0) w = a.diag[c];
+            else if (WHAT == 1) { r = a.rD[pos]; w = r * a.rA[c]; a.B[pos] = sent; }
+            else { r = a.rD[pos]; w = a.F[pos]; a.F[pos] = sent; }
         }
-        int col[FG], gN = 0, k = 0;          // the group in registers: neighbour ids, coefficients, how many, how many consumed
+        int col[FG], gN = 0, k = 0;          // the group in registers: neighbour positions, coefficients, how many, how many consumed
         double coef[FG];
         auto load_group = [&]() {
             gN = min(FG, left); k = 0;
@@ -84,11 +116,8 @@ __global__ void __launch_bounds__(BLK) k_sweep_flow(FlowArgs a)
             for (int q = 0; q < FG; q++) {
                 col[q] = 0; coef[q] = 0.0;
                 if (q < gN) {
-                    const int idx = WHAT == 2 ? e - q : e + q;
-                    const int f = a.rowFace[idx];
-                    col[q] = a.rowCol[idx];
-                    if (WHAT == 0) coef[q] = DILU ? a.upper[f] * a.lower[f] : a.upper[f] * a.upper[f];
-                    else coef[q] = r * ((WHAT == 1 && DILU) ? a.lower[f] : a.upper[f]);
+                    col[q] = nbr[e + q];
+                    coef[q] = WHAT == 0 ? cf[e + q] : r * cf[e + q];
                 }
             }
         };
@@ -109,12 +138,13 @@ __global__ void __launch_bounds__(BLK) k_sweep_flow(FlowArgs a)
                     }
                 }
                 if (k == gN) {
-                    left -= gN; e = WHAT == 2 ? e - gN : e + gN;
-                    if (left == 0) { st_relaxed_f64(out + c, w); done = true; }
+                    left -= gN; e += gN;
+                    if (left == 0) { st_relaxed_f64(out + pos, w); done = true; }
                     else load_group();
                 }
             }
         }
+        if (WHAT == 2 && act) a.wA[c] = w;
         if (DOT) {
             const double part = warp_reduce<Sum>(act ? w * a.dotVec[c] : 0.0);
             if (lane == 0) a.chunkPartial[chunk] = part;

@@ -75,6 +75,29 @@ Ldu::Ldu(Ctx* c, int nCells_, int nFaces_, const int* lower, const int* upper, i
         useFlow = !(e && std::string(e) == "coop");
     }
     cudaStream_t s = ctx->stream;
+    if (useFlow && nCells > 0) {
+        // dependency tables of the barrier-free sweeps, in position (= level) order with neighbour POSITIONS:
+        // lower-side faces ascending (forward / factor), owned faces descending (backward)
+        std::vector<int> posOf(nCells);
+        for (int p = 0; p < nCells; p++) posOf[lvlCells[p]] = p;
+        std::vector<int> fStart(nCells + 1, 0), bStart(nCells + 1, 0), fPos(nFaces), fFace(nFaces), bPos(nFaces), bFace(nFaces);
+        for (int p = 0; p < nCells; p++) {
+            const int cI = lvlCells[p];
+            fStart[p + 1] = fStart[p] + (rowMid[cI] - rowStart[cI]);
+            bStart[p + 1] = bStart[p] + (rowStart[cI + 1] - rowMid[cI]);
+            int o = fStart[p];
+            for (int e = rowStart[cI]; e < rowMid[cI]; e++, o++) { fPos[o] = posOf[rowCol[e]]; fFace[o] = rowFace[e]; }
+            o = bStart[p];
+            for (int e = rowStart[cI + 1] - 1; e >= rowMid[cI]; e--, o++) { bPos[o] = posOf[rowCol[e]]; bFace[o] = rowFace[e]; }
+        }
+        d_fStart = dev_alloc<int>(nCells + 1); d_bStart = dev_alloc<int>(nCells + 1);
+        d_fPos = dev_alloc<int>(std::max(nFaces, 1)); d_fFace = dev_alloc<int>(std::max(nFaces, 1));
+        d_bPos = dev_alloc<int>(std::max(nFaces, 1)); d_bFace = dev_alloc<int>(std::max(nFaces, 1));
+        h2d(d_fStart, fStart.data(), nCells + 1, s); h2d(d_bStart, bStart.data(), nCells + 1, s);
+        h2d(d_fPos, fPos.data(), nFaces, s); h2d(d_fFace, fFace.data(), nFaces, s);
+        h2d(d_bPos, bPos.data(), nFaces, s); h2d(d_bFace, bFace.data(), nFaces, s);
+        ctx->sync();                                         // the staging vectors go out of scope here
+    }
     d_lower = dev_alloc<int>(nFaces); d_upper = dev_alloc<int>(nFaces);
     d_rowStart = dev_alloc<int>(nCells + 1); d_rowMid = dev_alloc<int>(nCells);
     d_rowCol = dev_alloc<int>(2 * (size_t)nFaces); d_rowFace = dev_alloc<int>(2 * (size_t)nFaces);
@@ -123,7 +146,9 @@ Ldu::~Ldu()
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
     dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace);
-    dev_free(flowF); dev_free(flowPartial); dev_free(flowTicket);
+    dev_free(d_fStart); dev_free(d_fPos); dev_free(d_fFace); dev_free(d_bStart); dev_free(d_bPos); dev_free(d_bFace);
+    dev_free(flowCoefF); dev_free(flowCoefB); dev_free(flowNumF); dev_free(flowRD); dev_free(flowF); dev_free(flowB);
+    dev_free(flowPartial); dev_free(flowTicket);
 }
 
 void Ldu::setBlock(int nx, int ny, int nz)
@@ -469,12 +494,26 @@ void Ldu::factor(int kind, const MatrixView& A)
             if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
             else coop_launch(ctx, k_sweep_block<0, false, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
         } else if (useFlow) {
-            // raw recurrence values into a sentinel-filled rD; the forward scratch is reset here too, once per solve
+            // coefficients into the position-ordered tables, then the raw recurrence into a sentinel-filled rD; the sweeps'
+            // exchange arrays are reset here too, once per solve
             const int grid = std::max(1, std::min(redBlocks, (nCells + BLK - 1) / BLK));
-            if (!flowF) flowF = dev_alloc<double>((size_t)std::max(nCells, 1));
-            k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, rd, st); B200_LAUNCH_CHECK();
+            if (!flowF) {
+                const size_t nn = (size_t)std::max(nCells, 1), nf = (size_t)std::max(nFaces, 1);
+                flowF = dev_alloc<double>(nn); flowB = dev_alloc<double>(nn); flowRD = dev_alloc<double>(nn);
+                flowCoefF = dev_alloc<double>(nf); flowCoefB = dev_alloc<double>(nf); flowNumF = dev_alloc<double>(nf);
+            }
+            if (nFaces > 0) {
+                const int gg = std::max(1, std::min(redBlocks, (nFaces + BLK - 1) / BLK));
+                if (dilu) k_flow_gather<true><<<gg, BLK, 0, s>>>(nFaces, d_fFace, d_bFace, A.upper, A.lower, flowCoefF, flowCoefB, flowNumF, st);
+                else k_flow_gather<false><<<gg, BLK, 0, s>>>(nFaces, d_fFace, d_bFace, A.upper, A.lower, flowCoefF, flowCoefB, flowNumF, st);
+                B200_LAUNCH_CHECK();
+            }
+            k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowRD, st); B200_LAUNCH_CHECK();
             k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowF, st); B200_LAUNCH_CHECK();
+            k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowB, st); B200_LAUNCH_CHECK();
             flowSweep(0, dilu, false, A, nullptr, nullptr, nullptr);
+            k_reciprocal<<<redBlocks, BLK, 0, s>>>((int64_t)nCells, flowRD, st); B200_LAUNCH_CHECK();
+            return;              // rD lives in position order (flowRD)
         } else {
             const int* ls = d_lvlStart;
             if (dilu) coop_launch(ctx, k_sweep_general<0, true, false>, (int64_t)maxLevelSize, nLevels, ls, (const int*)d_lvlCells, (const int*)d_rowStart, (const int*)d_rowMid, (const int*)d_rowCol, (const int*)d_rowFace, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
@@ -492,12 +531,14 @@ void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const do
     if (nChunks == 0) return;
     if (!flowTicket) { flowTicket = dev_alloc<int>(1); flowPartial = dev_alloc<double>((size_t)nChunks); }
     FlowArgs a;
-    a.n = nCells; a.lvlCells = d_lvlCells; a.rowStart = d_rowStart; a.rowMid = d_rowMid; a.rowCol = d_rowCol; a.rowFace = d_rowFace;
-    a.diag = A.diag; a.upper = A.upper; a.lower = A.lower; a.rD = rD + ghost; a.rA = rA; a.F = flowF; a.wA = wA; a.dotVec = dotVec;
+    (void)dilu;                    // the coefficient tables were gathered for DIC or DILU by factor()
+    a.n = nCells; a.perm = d_lvlCells; a.fStart = d_fStart; a.fPos = d_fPos; a.bStart = d_bStart; a.bPos = d_bPos;
+    a.coefF = flowCoefF; a.coefB = flowCoefB; a.numF = flowNumF;
+    a.diag = A.diag; a.rD = flowRD; a.rA = rA; a.F = flowF; a.B = flowB; a.wA = wA; a.dotVec = dotVec;
     a.chunkPartial = flowPartial; a.ticket = flowTicket; a.st = d_state;
     static int perSM = 0;
     if (!perSM) {
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sweep_flow<2, false, true>, BLK, 0));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_sweep_flow<2, true>, BLK, 0));
         perSM = std::max(perSM, 1);
     }
     static const int envBlocks = [] { const char* e = std::getenv("B200_FLOW_BLOCKS"); return e ? std::atoi(e) : 0; }();
@@ -506,16 +547,10 @@ void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const do
     // few warps in flight: the ones far ahead of the front only poll, and their polls are L2 traffic the front has to queue behind
     const int grid = std::min((nChunks + BLK / 32 - 1) / (BLK / 32), ctx->smCount * std::min(envBlocks > 0 ? envBlocks : 2, perSM));
     B200_CUDA(cudaMemsetAsync(flowTicket, 0, sizeof(int), s));
-    if (what == 0) {
-        if (dilu) k_sweep_flow<0, true, false><<<grid, BLK, 0, s>>>(a);
-        else k_sweep_flow<0, false, false><<<grid, BLK, 0, s>>>(a);
-    } else if (what == 1) {
-        if (dilu) k_sweep_flow<1, true, false><<<grid, BLK, 0, s>>>(a);
-        else k_sweep_flow<1, false, false><<<grid, BLK, 0, s>>>(a);
-    } else {
-        if (dot) k_sweep_flow<2, false, true><<<grid, BLK, 0, s>>>(a);
-        else k_sweep_flow<2, false, false><<<grid, BLK, 0, s>>>(a);
-    }
+    if (what == 0) k_sweep_flow<0, false><<<grid, BLK, 0, s>>>(a);
+    else if (what == 1) k_sweep_flow<1, false><<<grid, BLK, 0, s>>>(a);
+    else if (dot) k_sweep_flow<2, true><<<grid, BLK, 0, s>>>(a);
+    else k_sweep_flow<2, false><<<grid, BLK, 0, s>>>(a);
     B200_LAUNCH_CHECK();
     if (what == 2 && dot) { k_sum<<<red_blocks_for(nChunks), BLK, 0, s>>>((int64_t)nChunks, flowPartial, red, (int)S_RHO, d_state); B200_LAUNCH_CHECK(); }
 }

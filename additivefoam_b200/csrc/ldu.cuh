@@ -127,7 +127,10 @@ public:
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;
     // barrier-free level-ordered sweeps over general addressing (flow_kernels.cuh)
     bool useFlow = true;
-    double* flowF = nullptr;         // forward result, all sentinel between applications
+    int *d_fStart = nullptr, *d_fPos = nullptr, *d_fFace = nullptr;   // position-ordered dependency tables (see FlowArgs)
+    int *d_bStart = nullptr, *d_bPos = nullptr, *d_bFace = nullptr;
+    double *flowCoefF = nullptr, *flowCoefB = nullptr, *flowNumF = nullptr;   // coefficients gathered next to them, once per solve
+    double *flowRD = nullptr, *flowF = nullptr, *flowB = nullptr;             // position-ordered rD, forward and backward results
     double* flowPartial = nullptr;   // per-chunk sums of the fused dot product
     int* flowTicket = nullptr;
     void flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec);
