@@ -545,7 +545,7 @@ void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const do
     static const int envSleep = [] { const char* e = std::getenv("B200_FLOW_SLEEP"); return e ? std::atoi(e) : 0; }();
     a.sleepNs = envSleep;
     // few warps in flight: the ones far ahead of the front only poll, and their polls are L2 traffic the front has to queue behind
-    const int grid = std::min((nChunks + BLK / 32 - 1) / (BLK / 32), ctx->smCount * std::min(envBlocks > 0 ? envBlocks : 3, perSM));
+    const int grid = std::min((nChunks + BLK / 32 - 1) / (BLK / 32), ctx->smCount * std::min(envBlocks > 0 ? envBlocks : 2, perSM));
     B200_CUDA(cudaMemsetAsync(flowTicket, 0, sizeof(int), s));
     if (what == 0) k_sweep_flow<0, false><<<grid, BLK, 0, s>>>(a);
     else if (what == 1) k_sweep_flow<1, false><<<grid, BLK, 0, s>>>(a);
