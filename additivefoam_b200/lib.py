@@ -284,6 +284,16 @@ class Case:
         _check(self.L.b200_case_n_cells(self.h, C.byref(nl), C.byref(ng)))
         self.n_local, self.n_global = nl.value, ng.value
 
+    @classmethod
+    def from_case_dir(cls, ctx, case_dir, **overrides):
+        """A case straight from an AdditiveFOAM case directory (system/blockMeshDict, 0/T, constant/transportProperties,
+        thermoPath, heatSourceDict + scan paths, system/controlDict, fvSolution, setFieldsDict): see ``foamcase.read_case``.
+        ``overrides`` update the controls (e.g. ``explicitSolve=0, solver=abi.SOLVER_PCG``)."""
+        from . import foamcase
+        case = foamcase.read_case(case_dir)
+        case["controls"].update(overrides)
+        return cls(ctx, case)
+
     def running(self):
         return bool(self.L.b200_case_running(self.h))
 
