@@ -101,7 +101,11 @@ inline void buildMesh(Mesh& m, const b200_case_desc& d, int r, int R)
                 for (label i = 0; i < nx; i++) for (label j = 0; j < ny; j++) add(i + nx * (j + ny * k), m.dx * m.dy, 0.5 * m.dz);
             }
         }
-        pa.Tb.assign(pa.faceCells.size(), d.Tinitial);
+        // 0/T `value` entries: a fixedValue patch is constructed from its own `value` ([UPSTREAM] fixedValueFvPatchField reads
+        // it as the patch field), the others start from the entry the tutorials give them, the internal value.  (Until a case
+        // with a wall temperature different from the initial one was read from a directory, this started every patch from
+        // Tinitial: identical for all shipped cases, wrong for the first step otherwise -- found by tests/test_foam_case.py.)
+        pa.Tb.assign(pa.faceCells.size(), pa.type == B200_BC_FIXED_VALUE ? pa.fixedValue : d.Tinitial);
         pa.valueFraction.assign(pa.faceCells.size(), 0.0);
         m.patches.push_back(std::move(pa));
     }

@@ -84,3 +84,18 @@ def test_beam_switches_off_and_pool_solidifies(ctx, oracle):
     case["controls"]["endTime"] = 0.002
     T, r = compare(ctx, oracle, case, 110)
     assert r.totalPower == 0.0 and r.time > 0.000375
+
+
+@pytest.mark.parametrize("mode", ["implicit", "explicit"])
+@pytest.mark.parametrize("walls", ["base", "sides", "all"])
+def test_wall_temperature_differs_from_initial_temperature(ctx, oracle, mode, walls):
+    """fixedValue walls at 290 K around a 300 K block: the first step already sees the wall value (a fixedValue patch is
+    constructed from its own `value` entry).  All shipped cases have wall = initial temperature, which hid an oracle bug."""
+    kw = IMPLICIT if mode == "implicit" else dict()
+    case = cases.amb2018_02_b(n=(20, 8, 6), **kw)
+    if walls in ("base", "all"):
+        case["patches"][0] = cases._patch(abi.BC_FIXED_VALUE, [abi.ZMIN], value=290.0)
+    if walls in ("sides", "all"):
+        case["patches"][2] = cases._patch(abi.BC_FIXED_VALUE, [abi.XMIN, abi.XMAX, abi.YMIN, abi.YMAX], value=290.0)
+    T, r = compare(ctx, oracle, case, 15)
+    assert T.min() < 299.9        # the walls do cool the block from the first step on
