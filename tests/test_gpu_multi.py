@@ -33,3 +33,13 @@ def test_two_rank_function_objects():
            "--master-port", "29534", os.path.join(ROOT, "tools", "run_multi.py"), "funcobj", "120"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_two_rank_random_cases():
+    """The seeded random cases of test_gpu_fuzz.py on two z-slabs against the oracle's emulation of two ranks."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29535", os.path.join(ROOT, "tools", "run_multi.py"), "fuzz", "16"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
