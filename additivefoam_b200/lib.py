@@ -206,34 +206,52 @@ class LduSolver:
     """``lduMatrix::solver`` on the GPU: addressing at construction, coefficients per ``solve``."""
 
     def __init__(self, ctx, lower, upper, n_cells, block=None, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC,
-                 tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000):
+                 tolerance=1e-6, relTol=0.0, minIter=0, maxIter=1000, interfaces=None):
+        """``interfaces``: processor patches of a decomposed case as ``[(neighbour rank, faceCells), ...]``
+        ([UPSTREAM] processorLduInterface::neighbProcNo(), lduAddressing::patchAddr(p)); the matching
+        ``interfaceBouCoeffs`` go to ``solve`` / ``amul`` as ``bou_coeffs``."""
         self.ctx, self.L = ctx, ctx.L
         self.lower = np.ascontiguousarray(lower, dtype=np.int32)
         self.upper = np.ascontiguousarray(upper, dtype=np.int32)
         self.n, self.nf = int(n_cells), len(self.lower)
         self.h = C.c_void_p()
-        _check(self.L.b200_ldu_create(ctx.h, self.n, self.nf, _P(self.lower), _P(self.upper), 0, None, None, None, C.byref(self.h)))
+        self.face_cells = [np.ascontiguousarray(fc, dtype=np.int32) for _, fc in (interfaces or [])]
+        ni = len(self.face_cells)
+        ranks = np.array([r for r, _ in (interfaces or [])], dtype=np.int32)
+        sizes = np.array([len(fc) for fc in self.face_cells], dtype=np.int32)
+        ptrs = (ip * max(ni, 1))(*[_P(fc) for fc in self.face_cells])
+        _check(self.L.b200_ldu_create(ctx.h, self.n, self.nf, _P(self.lower), _P(self.upper), ni, _P(ranks) if ni else None,
+                                      _P(sizes) if ni else None, ptrs if ni else None, C.byref(self.h)))
         if block is not None:
             _check(self.L.b200_ldu_set_block(self.h, *block))
         self.controls = dict(solver=solver, preconditioner=preconditioner, tolerance=tolerance, relTol=relTol,
                              minIter=minIter, maxIter=maxIter)
 
-    def solve(self, psi, source, diag, upper, lower=None, **kw):
+    def _bou(self, bou_coeffs):
+        if not self.face_cells:
+            return None, None
+        keep = [_f64(b) for b in bou_coeffs]
+        assert [len(b) for b in keep] == [len(fc) for fc in self.face_cells], "one coefficient per interface face"
+        return (dp * len(keep))(*[_P(b) for b in keep]), keep
+
+    def solve(self, psi, source, diag, upper, lower=None, bou_coeffs=None, **kw):
         c = dict(self.controls)
         c.update(kw)
         psi = _f64(psi).copy()
         perf = abi.SolverPerf()
         diag, upper, source = _f64(diag), _f64(upper), _f64(source)
         lower = None if lower is None else _f64(lower)
-        _check(self.L.b200_ldu_solve(self.h, c["solver"], c["preconditioner"], _P(diag), _P(upper), _P(lower), None, _P(source),
+        bou, _keep = self._bou(bou_coeffs)
+        _check(self.L.b200_ldu_solve(self.h, c["solver"], c["preconditioner"], _P(diag), _P(upper), _P(lower), bou, _P(source),
                                      _P(psi), c["tolerance"], c["relTol"], c["minIter"], c["maxIter"], C.byref(perf)))
         return psi, perf
 
-    def amul(self, psi, diag, upper, lower=None):
+    def amul(self, psi, diag, upper, lower=None, bou_coeffs=None):
         psi, diag, upper = _f64(psi), _f64(diag), _f64(upper)
         lower = None if lower is None else _f64(lower)
         out = np.empty(self.n)
-        _check(self.L.b200_ldu_amul(self.h, _P(diag), _P(upper), _P(lower), None, _P(psi), _P(out)))
+        bou, _keep = self._bou(bou_coeffs)
+        _check(self.L.b200_ldu_amul(self.h, _P(diag), _P(upper), _P(lower), bou, _P(psi), _P(out)))
         return out
 
     def precondition(self, kind, rA, diag, upper, lower=None):

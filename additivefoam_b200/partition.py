@@ -55,3 +55,35 @@ def enable_peer_allreduce(ctx, dist, device=None):
     out = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(ctx.nranks)]
     dist.all_gather(out, mine)
     ctx.peer_import(b"".join(bytes(o.cpu().tolist()) for o in out))
+
+
+def decompose_ldu(n_cells, lower, upper, diag, upper_coeffs, lower_coeffs, rank, nranks):
+    """One rank's share of a global LDU matrix, the way decomposePar hands it to the solver: the cells
+    [n*rank/nranks, n*(rank+1)/nranks) in their global order (which keeps the faces upper-triangular), the faces with both
+    ends inside as the local matrix, and one processor interface per neighbouring rank for the faces that were cut --
+    faceCells in global face order on both sides, so that the two sides' lists pair up, and
+    interfaceBouCoeffs = -(the coefficient that multiplied the remote cell): [UPSTREAM] lduMatrix::Amul subtracts
+    interfaceBouCoeffs * psi_neighbour.  Returns a dict; `lower_coeffs` may be None (symmetric)."""
+    lower, upper = np.asarray(lower), np.asarray(upper)
+    lc = upper_coeffs if lower_coeffs is None else lower_coeffs
+    bounds = [n_cells * r // nranks for r in range(nranks + 1)]
+    owner_of = lambda c: np.searchsorted(bounds, c, side="right") - 1      # noqa: E731
+    c0, c1 = bounds[rank], bounds[rank + 1]
+    rl, ru = owner_of(lower), owner_of(upper)
+    inside = (rl == rank) & (ru == rank)
+    out = dict(c0=c0, c1=c1, n=c1 - c0, lower=(lower[inside] - c0).astype(np.int32), upper=(upper[inside] - c0).astype(np.int32),
+               diag=np.ascontiguousarray(diag[c0:c1]), upper_coeffs=np.ascontiguousarray(upper_coeffs[inside]),
+               lower_coeffs=None if lower_coeffs is None else np.ascontiguousarray(lower_coeffs[inside]), interfaces=[], bou_coeffs=[])
+    for other in range(nranks):
+        if other == rank:
+            continue
+        mine_low = (rl == rank) & (ru == other)        # my cell is the lower address: it is multiplied by upper[f]
+        mine_up = (ru == rank) & (rl == other)         # my cell is the upper address: lower[f]
+        cut = mine_low | mine_up
+        if not cut.any():
+            continue
+        face_cells = np.where(mine_low, lower, upper)[cut] - c0
+        coeffs = -np.where(mine_low, upper_coeffs, lc)[cut]
+        out["interfaces"].append((other, face_cells.astype(np.int32)))
+        out["bou_coeffs"].append(np.ascontiguousarray(coeffs))
+    return out

@@ -43,3 +43,14 @@ def test_two_rank_random_cases():
            "--master-port", "29535", os.path.join(ROOT, "tools", "run_multi.py"), "fuzz", "16"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_two_rank_ldu_solver_with_processor_interfaces():
+    """b200_ldu_* with coupled interfaces (the decomposed bPCG seam): Amul and none/diagonal-preconditioned solves reproduce the
+    oracle's serial solve of the global matrix, block-local DIC/DILU solve the global system."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29537", os.path.join(ROOT, "tools", "run_multi_ldu.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "MULTILDU ALL OK" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]

@@ -444,3 +444,28 @@ def test_solidification_box_and_decomposition(oracle):
     key = lambda e: np.lexsort((e[:, 0], e[:, 1], e[:, 2], e[:, 3]))
     assert np.allclose(ea[key(ea)], eb[key(eb)], rtol=1e-9)
     a.close(); b.close()
+
+
+def test_ldu_decomposition_helper_reassembles_the_global_product():
+    """partition.decompose_ldu (local matrix + processor interfaces, what the decomposed solver seam receives):
+    the ranks' local products minus interfaceBouCoeffs * neighbour values add up to the global A x."""
+    import helpers
+    from additivefoam_b200 import partition
+    n = 500
+    lo, up = helpers.random_ldu_addressing(n, 1200, 5)
+    for asym in (False, True):
+        diag, upper, lower, x, _ = helpers.spd_coefficients(n, lo, up, seed=3, asym=asym)
+        want = helpers.dense_from_ldu(n, lo, up, diag, upper, lower) @ x
+        for R in (2, 3, 5):
+            parts = [partition.decompose_ldu(n, lo, up, diag, upper, lower, r, R) for r in range(R)]
+            got = np.zeros(n)
+            for r, d in enumerate(parts):
+                assert np.all(d["lower"] < d["upper"]) and np.all(np.diff(d["lower"]) >= 0)      # still upper-triangular order
+                y = helpers.dense_from_ldu(d["n"], d["lower"], d["upper"], d["diag"], d["upper_coeffs"], d["lower_coeffs"]) @ x[d["c0"]:d["c1"]]
+                for (other, fc), bc in zip(d["interfaces"], d["bou_coeffs"]):
+                    o = parts[other]
+                    nfc = next(f for rr, f in o["interfaces"] if rr == r)
+                    assert len(nfc) == len(fc)
+                    np.subtract.at(y, fc, bc * x[o["c0"] + nfc])
+                got[d["c0"]:d["c1"]] = y
+            assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))

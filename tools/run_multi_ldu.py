@@ -1,0 +1,88 @@
+"""Decomposed lduMatrix::solver (what a decomposed OpenFOAM case hands to bPCG: local matrix + processor interfaces) on
+>= 2 GPUs against the oracle's serial solve of the global matrix.
+Usage: torchrun --nproc-per-node N tools/run_multi_ldu.py
+Amul and the solvers whose preconditioner does not see the decomposition (none, diagonal) must reproduce the global
+solve; DIC/DILU are block-local as in the reference, so there the check is the global residual of the returned solution."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import helpers  # noqa: E402
+from additivefoam_b200 import abi, lib, partition  # noqa: E402
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+uid = partition.broadcast_unique_id(lib.nccl_unique_id, rank, dist, device="cuda")
+ctx = lib.Context(local, uid, rank, world)
+
+
+def gather(part, sizes):
+    mx = max(sizes)
+    buf = torch.zeros(mx, dtype=torch.float64, device="cuda")
+    buf[: part.size] = torch.from_numpy(np.ascontiguousarray(part)).cuda()
+    out = [torch.zeros(mx, dtype=torch.float64, device="cuda") for _ in range(world)]
+    dist.all_gather(out, buf)
+    return np.concatenate([o[:s].cpu().numpy() for o, s in zip(out, sizes)])
+
+
+ok, lines = True, []
+problems = [("chain+random 3000", 3000, helpers.random_ldu_addressing(3000, 7000, 31), False),
+            ("chain+random 20000 asym", 20000, helpers.random_ldu_addressing(20000, 50000, 32), True),
+            ("block 24x10x9", 24 * 10 * 9, helpers.block_addressing_np((24, 10, 9)), False)]
+for name, n, (lo, up), asym in problems:
+    diag, upper, lower, x, b = helpers.spd_coefficients(n, lo, up, seed=77, asym=asym)
+    d = partition.decompose_ldu(n, lo, up, diag, upper, lower, rank, world)
+    sizes = [n * (r + 1) // world - n * r // world for r in range(world)]
+    s = lib.LduSolver(ctx, d["lower"], d["upper"], d["n"], interfaces=d["interfaces"])
+    xs, bs = x[d["c0"]:d["c1"]], b[d["c0"]:d["c1"]]
+    y = gather(s.amul(xs, d["diag"], d["upper_coeffs"], d["lower_coeffs"], bou_coeffs=d["bou_coeffs"]), sizes)
+    results = {}
+    combos = [(abi.SOLVER_PCG, abi.PRECOND_DIAGONAL), (abi.SOLVER_PCG, abi.PRECOND_NONE), (abi.SOLVER_PCG, abi.PRECOND_DIC)] if not asym else \
+             [(abi.SOLVER_PBICGSTAB, abi.PRECOND_DIAGONAL), (abi.SOLVER_PBICGSTAB, abi.PRECOND_DILU)]
+    for solver, precond in combos:
+        psi, perf = s.solve(xs, bs, d["diag"], d["upper_coeffs"], d["lower_coeffs"], bou_coeffs=d["bou_coeffs"], solver=solver,
+                            preconditioner=precond, tolerance=1e-10, relTol=0.0, minIter=1, maxIter=80)
+        results[(solver, precond)] = (gather(psi, sizes), perf)
+    s.close()
+    if rank == 0:
+        import ctypes as C
+        import oracle_lib as ol
+        O, P = ol.load(), ol.P
+        yo = np.empty(n)
+        O.afo_ldu_amul(n, len(lo), P(lo), P(up), P(diag), P(upper), P(lower), P(x), P(yo))
+        eA = helpers.rel_linf(y, yo)
+        good = eA < 1e-13
+        msg = [f"amul {eA:.1e}"]
+        A = None
+        for (solver, precond), (psi, perf) in results.items():
+            if precond in (abi.PRECOND_DIAGONAL, abi.PRECOND_NONE):
+                ref = x.copy(); rperf = abi.SolverPerf(); log = np.empty(4096); nlog = C.c_int32()
+                O.afo_ldu_solve(n, len(lo), P(lo), P(up), P(diag), P(upper), P(lower), P(b), P(ref), solver, precond, 1e-10, 0.0, 1, 80,
+                                C.byref(rperf), P(log), 4096, C.byref(nlog))
+                e = helpers.rel_linf(psi, ref)
+                fine = e < 1e-9 and abs(perf.nIterations - rperf.nIterations) <= 1 and abs(perf.initialResidual - rperf.initialResidual) <= 1e-10 * rperf.initialResidual
+                msg.append(f"solver{solver}/precond{precond} {e:.1e} it {perf.nIterations}/{rperf.nIterations}")
+            else:      # block-local DIC/DILU: the solution must solve the global system
+                r = np.empty(n)
+                O.afo_ldu_amul(n, len(lo), P(lo), P(up), P(diag), P(upper), P(lower), P(psi), P(r))
+                e = float(np.linalg.norm(r - b) / np.linalg.norm(b))
+                fine = bool(perf.converged) and e < 1e-7
+                msg.append(f"solver{solver}/precond{precond} residual {e:.1e} it {perf.nIterations}")
+            good = good and fine
+        ok = ok and good
+        print(f"MULTILDU {name}: " + "; ".join(msg) + (" OK" if good else " FAIL"), flush=True)
+flag = torch.tensor([1.0 if ok else 0.0], device="cuda")
+dist.broadcast(flag, 0)
+if rank == 0:
+    print("MULTILDU ALL " + ("OK" if ok else "FAIL"), flush=True)
+ctx.close()
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if flag.item() == 1.0 else 1)
