@@ -1,0 +1,79 @@
+"""The beam shapes (weight, V0) and the table interpolation against values computed by the REFERENCE's own code
+(tests/golden/ref_models.json, made by tests/golden/make_ref_models_golden.py from oracle/_ref/refModels = the reference's
+superGaussian.C, modifiedSuperGaussian.C, projectedGaussian.C and interpolateXY.C compiled where they lie).  Checked: the
+oracle's restatement and the library's host functions (what the device kernel calls, b200_beam_shape_*).  Host code only."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from additivefoam_b200 import cases, lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+GOLD = json.load(open(os.path.join(HERE, "golden", "ref_models.json")))
+PATH = [[1, 0, 0, 0, 100.0, 0.0], [0, 1e-3, 0, 0, 100.0, 0.8]]
+
+
+def beam_of(s):
+    if s["kind"] == "super":
+        return cases.super_gaussian_beam(PATH, dims=s["dims"], k=s["k"])
+    if s["kind"] == "modified":
+        return cases.modified_super_gaussian_beam(PATH, dims=s["dims"], k=s["k"], m=s["m"])
+    return cases.projected_gaussian_beam(PATH, dims=s["dims"], A=s["A"], B=s["B"])
+
+
+def ulps(a, b):
+    if a == b:
+        return 0.0
+    return abs(a - b) / np.spacing(max(abs(a), abs(b)))
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["shapes"])))
+def test_shapes_match_the_reference_code(oracle, i):
+    s = GOLD["shapes"][i]
+    b = beam_of(s)
+    ob = cases.make_beam(b)
+    dims = np.array([s["dims"][0], s["dims"][1], s["depth"]])
+    want_v0 = float.fromhex(s["V0"])
+    # V0: products of the same factors; a different association of the product may cost an ulp or two
+    assert ulps(oracle.afo_shape_V0(C.byref(ob), ol.P(dims)), want_v0) <= 2
+    assert ulps(lib.beam_shape_V0(b, dims)[0], want_v0) <= 2
+    worst_o = worst_l = 0.0
+    for p, w in zip(s["points"], s["weights"]):
+        want = float.fromhex(w)
+        d = np.array(p)
+        got_o = oracle.afo_shape_weight(C.byref(ob), ol.P(dims), ol.P(d))
+        got_l = lib.beam_shape_weight(b, dims, d)
+        if want == 0.0:
+            assert got_o == 0.0 and got_l == 0.0
+        else:
+            worst_o, worst_l = max(worst_o, abs(got_o - want) / want), max(worst_l, abs(got_l - want) / want)
+    # exp(-x): an ulp of difference in x (operand order of the quotients) becomes x ulps of the result
+    assert worst_o < 1e-13 and worst_l < 1e-13, (worst_o, worst_l)
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["tables"])))
+def test_interpolateXY_matches_the_reference_code(oracle, i):
+    t = GOLD["tables"][i]
+    X, Y = np.array(t["x"]), np.array(t["y"])
+    for q, v in zip(t["queries"], t["values"]):
+        assert oracle.afo_interpolateXY(q, len(X), ol.P(X), ol.P(Y)) == float.fromhex(v), q       # same expression: bit for bit
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/applications/solvers/additiveFoam/interpolateXY/interpolateXY.C"),
+                    reason="the reference tree is only present in the build container")
+def test_golden_is_what_the_reference_code_computes(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_ref_models_golden as mk
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    s = mk.shape_requests()[3]
+    lines = [f"shape {s['kind']} {s['k']!r} {s['m']!r} {s['A']!r} {s['B']!r} {s['dims'][0]!r} {s['dims'][1]!r} {s['dims'][2]!r} {s['depth']!r} {len(s['points'])}"]
+    lines += [f"{p[0]!r} {p[1]!r} {p[2]!r}" for p in s["points"]]
+    ans = mk.ask(lines)
+    assert ans[0][3:] == GOLD["shapes"][3]["V0"] and ans[1:] == GOLD["shapes"][3]["weights"]
