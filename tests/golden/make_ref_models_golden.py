@@ -46,6 +46,38 @@ def table_requests():
     return out
 
 
+MATERIALS = {
+    "IN625": dict(kappa=[[8.275, 0.01472, 0.0], [4.889, 0.014743, 0.0], [-0.07707, 0.00075, 0.0]],
+                  Cp=[[579.28, 0.0, 0.0], [750.65, 0.0, 0.0], [747.568, 0.0, 0.0]]),
+    "curved": dict(kappa=[[9.1, 0.012, 1.5e-6], [5.5, 0.013, -4e-7], [0.3, 0.0009, 2e-7]],
+                   Cp=[[560.0, 0.11, 2e-5], [740.0, -0.02, 0.0], [330.0, 0.05, 1e-5]]),
+}
+TABLES = {"IN625": ([1410.0, 1620.0], [1.0, 0.0]), "curved": ([1650.0, 1580.0, 1490.0, 1400.0], [0.0, 0.35, 0.8, 1.0])}
+
+
+def liquidus_solidus(name):
+    """createFields.H:59-71 with the reference's own interpolateXY: Tliq = interpolateXY(0, y, x), Tsol = interpolateXY(1, y, x)."""
+    x, y = TABLES[name]
+    ans = ask([f"table {len(x)}"] + [f"{b!r} {a!r}" for a, b in zip(x, y)] + ["2", "0.0", "1.0"])
+    return float.fromhex(ans[0]), float.fromhex(ans[1])
+
+
+def cell_states(name, n=240):
+    rng = np.random.default_rng(11 if name == "IN625" else 12)
+    tliq, tsol = liquidus_solidus(name)
+    T = rng.uniform(250.0, 3800.0, n)
+    T[:n // 2] = rng.uniform(tsol - 120.0, tliq + 120.0, n // 2)          # half of them around the mushy zone
+    T[:8] = [tsol, tliq, 300.0, 2.0 * tliq, np.nextafter(tsol, 0), np.nextafter(tliq, 1e9), 299.0, 2.0 * tliq + 1.0]
+    T[8:8 + len(TABLES[name][0])] = TABLES[name][0]                          # the table nodes themselves
+    a1 = rng.uniform(0.0, 1.0, n)
+    a1[::5] = 1.0
+    a1[1::7] = 0.0
+    a1[2::11] = 1e-9            # below thermoTol 1e-8
+    a1[3::13] = 1.0 - 1e-9
+    a3 = (rng.uniform(0.0, 1.0, n) < 0.4).astype(float)
+    return tliq, tsol, T.tolist(), a1.tolist(), a3.tolist()          # python floats: repr() must be a plain number
+
+
 def ask(lines):
     out = subprocess.run([REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
     return [ln for ln in out if ln]
@@ -65,9 +97,22 @@ def main():
         lines = [f"table {len(t['x'])}"] + [f"{a!r} {b!r}" for a, b in zip(t["x"], t["y"])] + [str(len(t["queries"]))] + [repr(q) for q in t["queries"]]
         t["values"] = ask(lines)
         assert len(t["values"]) == len(t["queries"])
+    cells = []
+    for name in MATERIALS:
+        tliq, tsol, T, a1, a3 = cell_states(name)
+        m = MATERIALS[name]
+        coeffs = " ".join(repr(v) for row in m["kappa"] + m["Cp"] for v in row)
+        ans = ask([f"props {len(T)} {tsol!r} {tliq!r}", coeffs] + [f"{t!r} {x!r} {y!r}" for t, x, y in zip(T, a1, a3)])
+        rec = dict(material=name, Tliq=tliq.hex(), Tsol=tsol.hex(), T=T, alpha1=a1, alpha3=a3,
+                   kappa=[r.split()[0] for r in ans], Cp=[r.split()[1] for r in ans], alpha3_after=[r.split()[2] for r in ans])
+        x, y = TABLES[name]
+        for tol in (1e-8, 1e-6):
+            ans = ask([f"source {len(T)} {tliq!r} {tsol!r} {tol!r} {len(x)}"] + [f"{a!r} {b!r}" for a, b in zip(x, y)] + [f"{t!r} {v!r}" for t, v in zip(T, a1)])
+            rec[f"dFdT_{tol:g}"], rec[f"T0_{tol:g}"] = [r.split()[0] for r in ans], [r.split()[1] for r in ans]
+        cells.append(rec)
     with open(os.path.join(HERE, "ref_models.json"), "w") as f:
-        json.dump(dict(shapes=shapes, tables=tables), f, indent=0)
-    print("shapes", len(shapes), "tables", len(tables), os.path.getsize(os.path.join(HERE, "ref_models.json")), "bytes")
+        json.dump(dict(shapes=shapes, tables=tables, cells=cells), f, indent=0)
+    print("shapes", len(shapes), "tables", len(tables), "cell sets", len(cells), os.path.getsize(os.path.join(HERE, "ref_models.json")), "bytes")
 
 
 if __name__ == "__main__":

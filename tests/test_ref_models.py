@@ -77,3 +77,60 @@ def test_golden_is_what_the_reference_code_computes(tmp_path):
     lines += [f"{p[0]!r} {p[1]!r} {p[2]!r}" for p in s["points"]]
     ans = mk.ask(lines)
     assert ans[0][3:] == GOLD["shapes"][3]["V0"] and ans[1:] == GOLD["shapes"][3]["weights"]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The per-cell fragments of the time loop -- updateProperties.H (kappa, Cp, powder reset) and thermo/thermoSource.H (dFdT, T0) --
+# as the REFERENCE's own text computes them (included verbatim into oracle/_ref/refModels), against the oracle and the CUDA
+# kernels (k_props, k_corrector) through the case API: upload T / alpha.solid / alpha.powder, take one step with a single
+# corrector, read kappa, Cp, alpha.powder, dFdT, T0 back.
+def cell_case(rec, tol, explicit):
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_ref_models_golden as mk
+    from additivefoam_b200 import abi
+    n = len(rec["T"])
+    case = cases.amb2018_02_b(n=(n, 1, 1), explicitSolve=1 if explicit else 0, maxDi=1e30, solver=abi.SOLVER_PCG,
+                              preconditioner=abi.PRECOND_DIAGONAL, nThermoCorrectors=1, thermoTolerance=tol, deltaT=1e-9, adjustTimeStep=0)
+    case["beams"] = []
+    m = mk.MATERIALS[rec["material"]]
+    x, y = mk.TABLES[rec["material"]]
+    case["material"].update(kappa=m["kappa"], Cp=m["Cp"], thermoT=list(x), thermoAlpha=list(y))
+    return case
+
+
+def check_cells(make, rec, tol):
+    from additivefoam_b200 import abi
+    for explicit in (False, True):
+        c = make(cell_case(rec, tol, explicit))
+        c.set_field(abi.FIELD_T, np.array(rec["T"]))
+        c.set_field(abi.FIELD_ALPHA_SOLID, np.array(rec["alpha1"]))
+        c.set_field(abi.FIELD_ALPHA_POWDER, np.array(rec["alpha3"]))
+        rep = c.step()
+        assert rep.nThermoCorr == 1 and rep.explicitStep == int(explicit)
+        want = lambda key: np.array([float.fromhex(v) for v in rec[key]])      # noqa: E731
+        # kappa, Cp: sums of products in the fragment's order, no transcendental function: bit for bit
+        assert np.array_equal(c.field(abi.FIELD_KAPPA), want("kappa"))
+        assert np.array_equal(c.field(abi.FIELD_CP), want("Cp"))
+        assert np.array_equal(c.field(abi.FIELD_ALPHA_POWDER), want("alpha3_after"))
+        if not explicit:        # the explicit pass fuses the solve and the alpha update; dFdT and T0 are not stored there
+            # a temperature exactly on an interior row of the table gives lo == hi and dFdT = 0/0 in the reference's text;
+            # the restatements reproduce that NaN rather than repairing it
+            assert np.array_equal(c.field(abi.FIELD_DFDT), want(f"dFdT_{tol:g}"), equal_nan=True)
+            assert np.array_equal(c.field(abi.FIELD_T0), want(f"T0_{tol:g}"), equal_nan=True)
+        c.close()
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["cells"])))
+@pytest.mark.parametrize("tol", [1e-8, 1e-6])
+def test_oracle_cell_fragments_match_the_reference_text(oracle, i, tol):
+    rec = GOLD["cells"][i]
+    assert float.fromhex(rec["Tliq"]) == max(rec["T"][:2]) and float.fromhex(rec["Tsol"]) == min(rec["T"][:2])
+    check_cells(lambda case: ol.OracleCase(case, lib=oracle), rec, tol)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(GOLD["cells"])))
+@pytest.mark.parametrize("tol", [1e-8, 1e-6])
+def test_gpu_cell_fragments_match_the_reference_text(ctx, i, tol):
+    check_cells(lambda case: lib.Case(ctx, case), GOLD["cells"][i], tol)
