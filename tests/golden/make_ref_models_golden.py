@@ -79,6 +79,7 @@ def cell_states(name, n=240):
 
 
 def ask(lines):
+    assert not any("np." in ln for ln in lines), "numpy scalars print as np.float64(...): convert to float first"
     out = subprocess.run([REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
     return [ln for ln in out if ln]
 
