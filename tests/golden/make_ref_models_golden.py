@@ -111,8 +111,19 @@ def main():
             ans = ask([f"source {len(T)} {tliq!r} {tsol!r} {tol!r} {len(x)}"] + [f"{a!r} {b!r}" for a, b in zip(x, y)] + [f"{t!r} {v!r}" for t, v in zip(T, a1)])
             rec[f"dFdT_{tol:g}"], rec[f"T0_{tol:g}"] = [r.split()[0] for r in ans], [r.split()[1] for r in ans]
         cells.append(rec)
+    # absorptionModels/Kelly/KellyAbsorption.C compiled into oracle/_ref/refKelly
+    rng = np.random.default_rng(5)
+    kelly = []
+    for geometry, eta0, eta_min in (("cone", 0.28, 0.35), ("cylinder", 0.28, 0.35), ("cone", 0.41, 0.3), ("cylinder", 0.12, 0.2)):
+        ratios = [0.3, 0.75, 1.0, float(np.nextafter(1.0, 2.0)), 1.0000001, 2.0, 7.5, 40.0] + rng.uniform(0.2, 12.0, 24).tolist()
+        lines = [f"kelly {geometry} {eta0!r} {eta_min!r} {len(ratios)}"] + [repr(a) for a in ratios]
+        assert not any("np." in ln for ln in lines)
+        out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "refKelly")], input="\n".join(lines) + "\n", capture_output=True, text=True,
+                             check=True).stdout.split()
+        assert len(out) == len(ratios)
+        kelly.append(dict(geometry=geometry, eta0=eta0, etaMin=eta_min, ratios=ratios, eta=out))
     with open(os.path.join(HERE, "ref_models.json"), "w") as f:
-        json.dump(dict(shapes=shapes, tables=tables, cells=cells), f, indent=0)
+        json.dump(dict(shapes=shapes, tables=tables, cells=cells, kelly=kelly), f, indent=0)
     print("shapes", len(shapes), "tables", len(tables), "cell sets", len(cells), os.path.getsize(os.path.join(HERE, "ref_models.json")), "bytes")
 
 

@@ -134,3 +134,18 @@ def test_oracle_cell_fragments_match_the_reference_text(oracle, i, tol):
 @pytest.mark.parametrize("tol", [1e-8, 1e-6])
 def test_gpu_cell_fragments_match_the_reference_text(ctx, i, tol):
     check_cells(lambda case: lib.Case(ctx, case), GOLD["cells"][i], tol)
+
+
+@pytest.mark.parametrize("i", range(len(GOLD["kelly"])))
+def test_kelly_absorption_matches_the_reference_code(oracle, i):
+    """absorptionModels/Kelly/KellyAbsorption.C (compiled into oracle/_ref/refKelly): cone and cylinder, the discontinuity at
+    aspect ratio 1, against the oracle's restatement and the library's host function."""
+    from additivefoam_b200 import abi
+    k = GOLD["kelly"][i]
+    b = cases.modified_super_gaussian_beam(PATH, eta0=k["eta0"], etaMin=k["etaMin"])
+    b["kellyGeometry"] = abi.KELLY_CONE if k["geometry"] == "cone" else abi.KELLY_CYLINDER
+    ob = cases.make_beam(b)
+    for a, e in zip(k["ratios"], k["eta"]):
+        want = float.fromhex(e)
+        assert oracle.afo_absorption_eta(C.byref(ob), a) == want, a          # same expression: bit for bit
+        assert lib.beam_absorption_eta(b, a) == want, a
