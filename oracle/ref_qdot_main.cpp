@@ -1,0 +1,93 @@
+// Driver around the REFERENCE's own heat-source integration, compiled where it lies:
+//   movingHeatSource/heatSourceModels/heatSourceModel/heatSourceModel.C     constructor (:75-118), updateDimensions (:123-219),
+//                                                                           qDot (:221-371)
+//   .../superGaussian/superGaussian.C, modifiedSuperGaussian.C, projectedGaussian.C   (weight, V0)
+// against the REAL heatSourceModel.H and the stand-ins of oracle/ref_stubs/hsm (one uniform hex block for fvMesh; what else
+// is emulated is listed in hsmStub.H).  Request on stdin:
+//   qdot <super|modified|projected> k m A B  dimX dimY dimZ  depth  nPx nPy nPz  eta power  posX posY posZ  nx ny nz  minX minY minZ  maxX maxY maxZ
+// -> "sum <hex>" (the Riemann sum of V*weight actually used is not exposed; printed is sum(V*qDot)), then nx*ny*nz hex floats qDot.
+// Built by oracle/Makefile into oracle/_ref/refQDot when /root/reference is present.  TEST INFRASTRUCTURE ONLY: it produces
+// tests/golden/ref_qdot.json (tests/golden/make_ref_qdot_golden.py).
+#include "heatSourceModel.C"
+#include "superGaussian.C"
+#include "modifiedSuperGaussian.C"
+#include "projectedGaussian.C"
+
+#include <cstdio>
+#include <iostream>
+
+namespace Foam
+{
+static movingBeam theBeam;
+static absorptionModel theAbsorption;
+autoPtr<movingBeam> movingBeam::New(const word&, const dictionary&, const Time&) { return autoPtr<movingBeam>(&theBeam); }
+autoPtr<absorptionModel> absorptionModel::New(const word&, const dictionary&, const fvMesh&) { return autoPtr<absorptionModel>(&theAbsorption); }
+
+// [UPSTREAM] blockMesh for one uniform block: points min + i*d (x fastest), cells x fastest, hex cell -> its 8 points,
+// internal faces in upper-triangular order (per cell: +x, +y, +z neighbours)
+void fvMesh::build(label NX, label NY, label NZ, const vector& lo, const vector& hi)
+{
+    nx = NX; ny = NY; nz = NZ;
+    const vector d((hi.x() - lo.x()) / NX, (hi.y() - lo.y()) / NY, (hi.z() - lo.z()) / NZ);
+    for (label k = 0; k <= NZ; k++) for (label j = 0; j <= NY; j++) for (label i = 0; i <= NX; i++)
+        points_.push_back(point(lo.x() + i * d.x(), lo.y() + j * d.y(), lo.z() + k * d.z()));
+    auto pid = [&](label i, label j, label k) { return i + (NX + 1) * (j + (NY + 1) * k); };
+    static volVectorField cc;
+    cc.clear();
+    for (label k = 0; k < NZ; k++) for (label j = 0; j < NY; j++) for (label i = 0; i < NX; i++) {
+        labelList v;
+        for (label c = 0; c < 8; c++) v.push_back(pid(i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1)));
+        cellPoints_.push_back(v);
+        V_.push_back(d.x() * d.y() * d.z());
+        const vector centre(lo.x() + (i + 0.5) * d.x(), lo.y() + (j + 0.5) * d.y(), lo.z() + (k + 0.5) * d.z());
+        cc_.push_back(centre); cc.push_back(centre);
+        const label c0 = i + NX * (j + NY * k);
+        if (i < NX - 1) { owner_.push_back(c0); neighbour_.push_back(c0 + 1); }
+        if (j < NY - 1) { owner_.push_back(c0); neighbour_.push_back(c0 + NX); }
+        if (k < NZ - 1) { owner_.push_back(c0); neighbour_.push_back(c0 + NX * NY); }
+    }
+    C_ = &cc;
+}
+const fvMesh* theMesh = nullptr;
+dimensionedScalar fvc::domainIntegrate(const volScalarField& f)
+{
+    scalar s = 0;
+    forAll(f, i) s += theMesh->V()[i] * f[i];
+    return dimensionedScalar(s);
+}
+}
+
+int main()
+{
+    using namespace Foam;
+    std::string what, kind;
+    while (std::cin >> what >> kind) {
+        if (what != "qdot") return 2;
+        std::string k, m, A, B, dx, dy, dz, npx, npy, npz;
+        double depth, eta, power, px, py, pz, lox, loy, loz, hix, hiy, hiz;
+        int nx, ny, nz;
+        std::cin >> k >> m >> A >> B >> dx >> dy >> dz >> depth >> npx >> npy >> npz >> eta >> power >> px >> py >> pz >> nx >> ny >> nz
+                 >> lox >> loy >> loz >> hix >> hiy >> hiz;
+        refEntries() = {{"k", k}, {"m", m}, {"A", A}, {"B", B}, {"dimensions", dx + " " + dy + " " + dz}, {"nPoints", npx + " " + npy + " " + npz}};
+        fvMesh mesh;
+        mesh.build(nx, ny, nz, vector(lox, loy, loz), vector(hix, hiy, hiz));
+        theMesh = &mesh;
+        theBeam.position_ = vector(px, py, pz); theBeam.power_ = power; theAbsorption.eta_ = eta;
+        dictionary dict;
+        heatSourceModel* model = nullptr;
+        if (kind == "super") model = new heatSourceModels::superGaussian("beam", dict, mesh);
+        else if (kind == "modified") model = new heatSourceModels::modifiedSuperGaussian("beam", dict, mesh);
+        else model = new heatSourceModels::projectedGaussian("beam", dict, mesh);
+        // a transient beam's current depth (what updateDimensions() would have set): through the public staticDimensions()/dimensions()
+        // there is no setter, so the depth is given as the z of `dimensions` and the static xy stay what they are
+        (void)depth;
+        tmp<volScalarField> tq = model->qDot();
+        const volScalarField& q = tq();
+        double sum = 0;
+        forAll(q, i) sum += mesh.V()[i] * q[i];
+        std::printf("sum %a\n", sum);
+        forAll(q, i) std::printf("%a\n", q[i]);
+        delete model;
+    }
+    return 0;
+}
