@@ -282,5 +282,17 @@ int64_t afo_case_solidification_events(void* h, scalar* out, int64_t maxEvents)
 scalar afo_case_time(void* h) { return ((Case*)h)->time; }
 scalar afo_case_Tliq(void* h) { return ((Case*)h)->Tliq; }
 scalar afo_case_Tsol(void* h) { return ((Case*)h)->Tsol; }
+// heatSourceModel::updateDimensions (heatSourceModel.C:123-219) of beam b on the case's current T with the beam centre at `position`:
+// the resulting dimensions (x, y static; z the isotherm depth).  The beam's own state is left as it was.
+int afo_case_isotherm_depth(void* h, int b, const scalar position[3], scalar dimsOut[3])
+{
+    Case* c = (Case*)h;
+    if (b < 0 || b >= (int)c->sources.size()) return 1;
+    HeatSource hs = c->sources[b];
+    hs.beam.position = {position[0], position[1], position[2]};
+    c->updateDimensions(hs);
+    dimsOut[0] = hs.shape.dimensions.x; dimsOut[1] = hs.shape.dimensions.y; dimsOut[2] = hs.shape.dimensions.z;
+    return 0;
+}
 
 } // extern "C"

@@ -62,6 +62,31 @@ int main()
     using namespace Foam;
     std::string what, kind;
     while (std::cin >> what >> kind) {
+        if (what == "depth") {
+            // depth <modified|projected> k m A B dimX dimY dimZ isoValue posX posY posZ nx ny nz minX minY minZ maxX maxY maxZ  then nx*ny*nz temperatures
+            // -> the dimensions after updateDimensions() (heatSourceModel.C:123-219)
+            std::string k, m, A, B, dx, dy, dz, iso;
+            double px, py, pz, lox, loy, loz, hix, hiy, hiz;
+            int nx, ny, nz;
+            std::cin >> k >> m >> A >> B >> dx >> dy >> dz >> iso >> px >> py >> pz >> nx >> ny >> nz >> lox >> loy >> loz >> hix >> hiy >> hiz;
+            refEntries() = {{"k", k}, {"m", m}, {"A", A}, {"B", B}, {"dimensions", dx + " " + dy + " " + dz}, {"transient", "1"}, {"isoValue", iso}};
+            fvMesh mesh;
+            mesh.build(nx, ny, nz, vector(lox, loy, loz), vector(hix, hiy, hiz));
+            theMesh = &mesh;
+            volScalarField T(nx * ny * nz);
+            forAll(T, i) std::cin >> T[i];
+            mesh.T_ = &T;
+            theBeam.position_ = vector(px, py, pz); theBeam.power_ = 1.0; theAbsorption.eta_ = 1.0;
+            dictionary dict;
+            heatSourceModel* model = nullptr;
+            if (kind == "modified") model = new heatSourceModels::modifiedSuperGaussian("beam", dict, mesh);
+            else model = new heatSourceModels::projectedGaussian("beam", dict, mesh);
+            model->updateDimensions();
+            const vector d = model->dimensions();
+            std::printf("%a %a %a\n", d.x(), d.y(), d.z());
+            delete model;
+            continue;
+        }
         if (what != "qdot") return 2;
         std::string k, m, A, B, dx, dy, dz, npx, npy, npz;
         double depth, eta, power, px, py, pz, lox, loy, loz, hix, hiy, hiz;

@@ -28,6 +28,53 @@ CASES = [
 ]
 
 
+# updateDimensions(): kind, k, m, A, B, static dimensions, isoValue, beam position, mesh n, min, max, hot-spot (centre, radii, peak)
+DEPTH_CASES = [
+    ("modified", 7.95, 2.72, 0, 0, (40e-6, 40e-6, 30e-6), 1620.0, (2.0e-4, 1.5e-4, 2.4e-4), (20, 15, 12), (0, 0, 0), (4e-4, 3e-4, 2.4e-4),
+     ((2.07e-4, 1.46e-4, 2.4e-4), (70e-6, 60e-6, 95e-6), 3100.0)),
+    ("projected", 0, 0, 2.0, 1.0, (50e-6, 50e-6, 30e-6), 1500.0, (2.2e-4, 1.4e-4, 2.4e-4), (20, 15, 12), (0, 0, 0), (4e-4, 3e-4, 2.4e-4),
+     ((2.1e-4, 1.5e-4, 2.4e-4), (90e-6, 50e-6, 150e-6), 2600.0)),
+    # the pool is shallower than the static depth: the depth stays the static one
+    ("modified", 5.0, 2.0, 0, 0, (40e-6, 40e-6, 60e-6), 1620.0, (2.0e-4, 1.5e-4, 2.4e-4), (20, 15, 12), (0, 0, 0), (4e-4, 3e-4, 2.4e-4),
+     ((2.0e-4, 1.5e-4, 2.4e-4), (60e-6, 60e-6, 25e-6), 2500.0)),
+    # the isotherm lies outside the search radius max(dx, dy) around the beam axis
+    ("modified", 5.0, 2.0, 0, 0, (30e-6, 30e-6, 20e-6), 1620.0, (0.8e-4, 1.5e-4, 2.4e-4), (20, 15, 12), (0, 0, 0), (4e-4, 3e-4, 2.4e-4),
+     ((3.0e-4, 1.5e-4, 2.4e-4), (50e-6, 50e-6, 120e-6), 3000.0)),
+    # non-cubic cells
+    ("projected", 0, 0, 1.0, 0.5, (45e-6, 60e-6, 25e-6), 1550.0, (3.0e-4, 1.0e-4, 1.9e-4), (25, 14, 9), (0, -1e-4, -1e-5), (6.5e-4, 3.2e-4, 2.0e-4),
+     ((3.05e-4, 1.1e-4, 1.9e-4), (80e-6, 70e-6, 110e-6), 2900.0)),
+]
+
+
+def hot_spot(n, lo, hi, spot):
+    """T at the cell centres (cell order x fastest): 300 + (peak - 300) exp(-sum(((c - centre)/radius)^2)).  Plain Python floats."""
+    import math
+    (cx, cy, cz), (rx, ry, rz), peak = spot
+    d = [(hi[q] - lo[q]) / n[q] for q in range(3)]
+    T = []
+    for k in range(n[2]):
+        for j in range(n[1]):
+            for i in range(n[0]):
+                x, y, z = lo[0] + (i + 0.5) * d[0], lo[1] + (j + 0.5) * d[1], lo[2] + (k + 0.5) * d[2]
+                T.append(300.0 + (peak - 300.0) * math.exp(-(((x - cx) / rx) ** 2 + ((y - cy) / ry) ** 2 + ((z - cz) / rz) ** 2)))
+    return T
+
+
+def depth_golden():
+    out = []
+    for kind, k, m, A, B, dims, iso, pos, n, lo, hi, spot in DEPTH_CASES:
+        f = lambda v: repr(float(v))      # noqa: E731
+        T = hot_spot(n, lo, hi, spot)
+        lines = [" ".join(["depth", kind, f(k), f(m), f(A), f(B)] + [f(v) for v in dims] + [f(iso)] + [f(v) for v in pos] + [str(v) for v in n]
+                          + [f(v) for v in lo] + [f(v) for v in hi])] + [repr(t) for t in T]
+        ans = subprocess.run([REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split()
+        assert len(ans) == 3
+        out.append(dict(kind=kind, k=k, m=m, A=A, B=B, dims=list(dims), isoValue=iso, position=list(pos), n=list(n), min=list(lo), max=list(hi),
+                        spot=[list(spot[0]), list(spot[1]), spot[2]], dimensions=ans))
+        print("depth", kind, [float.fromhex(v) for v in ans], "static", dims[2])
+    return out
+
+
 def main():
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     assert os.path.exists(REF), "oracle/_ref/refQDot was not built: /root/reference is needed"
@@ -44,7 +91,7 @@ def main():
                         min=list(lo), max=list(hi), power_deposited=ans[0][4:], cells=[i for i, _ in nz], qdot=[v for _, v in nz]))
         print(kind, n, "nonzero cells", len(nz), "deposited", float.fromhex(ans[0][4:]), "eta*P", eta * power)
     with open(os.path.join(HERE, "ref_qdot.json"), "w") as fjson:
-        json.dump(out, fjson, indent=0)
+        json.dump(dict(qdot=out, depth=depth_golden()), fjson, indent=0)
     print(os.path.getsize(os.path.join(HERE, "ref_qdot.json")), "bytes")
 
 

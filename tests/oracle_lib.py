@@ -38,6 +38,7 @@ def load():
     L.afo_case_solidification_events.argtypes = [C.c_void_p, dp, C.c_int64]
     L.afo_case_solidification_events.restype = C.c_int64
     L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
+    L.afo_case_isotherm_depth.argtypes = [C.c_void_p, C.c_int, dp, dp]
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
         getattr(L, f).restype = C.c_double
         getattr(L, f).argtypes = [C.c_void_p]

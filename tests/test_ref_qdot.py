@@ -14,7 +14,8 @@ import oracle_lib as ol
 from additivefoam_b200 import abi, cases, lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLD = json.load(open(os.path.join(HERE, "golden", "ref_qdot.json")))
+_ALL = json.load(open(os.path.join(HERE, "golden", "ref_qdot.json")))
+GOLD, DEPTH = _ALL["qdot"], _ALL["depth"]
 PATH = [[1, 0, 0, 0, 100.0, 0.0], [0, 1e-3, 0, 0, 100.0, 0.8]]
 
 
@@ -67,3 +68,26 @@ def test_gpu_qdot_matches_the_reference_code(ctx, i):
     # exp/pow of the device differ from glibc's by <= 1 ulp
     assert np.max(np.abs(got - want)) <= 1e-11 * scale
     assert absorbed == pytest.approx(g["eta"] * g["power"], rel=1e-14)
+
+
+@pytest.mark.parametrize("i", range(len(DEPTH)))
+def test_oracle_isotherm_depth_matches_the_reference_code(oracle, i):
+    """heatSourceModel::updateDimensions (heatSourceModel.C:123-219) as the reference's own code runs it on a hot-spot temperature
+    field: depth beyond, equal to and capped by the static one, isotherm outside the search radius, non-cubic cells.  The CUDA
+    kernel (k_isotherm_depth) is held to the oracle by the transient-beam cases of test_gpu_case.py / test_gpu_fuzz.py."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_ref_qdot_golden as mk
+    g = DEPTH[i]
+    if g["kind"] == "modified":
+        b = cases.modified_super_gaussian_beam(PATH, dims=g["dims"], k=g["k"], m=g["m"], transient=1, isoValue=g["isoValue"])
+    else:
+        b = cases.projected_gaussian_beam(PATH, dims=g["dims"], A=g["A"], B=g["B"], transient=1, isoValue=g["isoValue"])
+    case = cases.amb2018_02_b(n=tuple(g["n"]))
+    case["mesh"]["min"], case["mesh"]["max"], case["beams"] = g["min"], g["max"], [b]
+    o = ol.OracleCase(case, lib=oracle)
+    o.set_field(abi.FIELD_T, np.array(mk.hot_spot(g["n"], g["min"], g["max"], (g["spot"][0], g["spot"][1], g["spot"][2]))))
+    pos, dims = np.array(g["position"]), np.zeros(3)
+    assert oracle.afo_case_isotherm_depth(o.h, 0, ol.P(pos), ol.P(dims)) == 0
+    o.close()
+    assert list(dims) == [float.fromhex(v) for v in g["dimensions"]]        # same interpolation expression: bit for bit
