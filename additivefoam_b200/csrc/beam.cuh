@@ -31,6 +31,7 @@ public:
     void adjustDeltaT(double& dt, double now) const;                          // movingBeam.C:228-256
     int findIndex(double time) const;                                         // movingBeam.C:196-225
     const double* position() const { return position_; }
+    void setPosition(const double p[3]) { position_[0] = p[0]; position_[1] = p[1]; position_[2] = p[2]; }   // diagnostic probes only
     double power() const { return power_; }
     double deltaT() const { return deltaT_; }
     double endTime() const { return endTime_; }

@@ -348,6 +348,14 @@ int b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* iso
     c->p->meltPoolDimensions(nIso, isoValues, scanPathAngleDeg, dims);
     B200_CATCH
 }
+int b200_case_isotherm_depth(b200_case* c, int32_t beam, const double position[3], double dimensions[3])
+{
+    B200_TRY
+    B200_CHECK(c && position && dimensions, "isotherm_depth: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->isothermDepthProbe(beam, position, dimensions);
+    B200_CATCH
+}
 int b200_case_solidification_enable(b200_case* c, const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents)
 {
     B200_TRY

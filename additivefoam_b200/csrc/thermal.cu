@@ -364,6 +364,16 @@ void ThermalCase::updateDimensions(heatSourceModel& hs)
     hs.dimensions[0] = hs.staticDimensions[0]; hs.dimensions[1] = hs.staticDimensions[1]; hs.dimensions[2] = h_red[R_DEPTH];
 }
 
+// updateDimensions of beam `beam` on the current T with the beam centre at `position`; the beam's own state is left as it was
+void ThermalCase::isothermDepthProbe(int beam, const double position[3], double dimensionsOut[3])
+{
+    B200_CHECK(beam >= 0 && beam < (int)sources.size(), "beam index out of range");
+    heatSourceModel hs = sources[beam];
+    hs.beam.setPosition(position);
+    updateDimensions(hs);
+    for (int q = 0; q < 3; q++) dimensionsOut[q] = hs.dimensions[q];
+}
+
 // heatSourceModel::qDot() for the beam's current position/power, accumulated as movingHeatSourceModel::update does
 void ThermalCase::qDotOnce(heatSourceModel& hs, double* target, double dt, double sumDt, bool directMean)
 {

@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
-    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_solidification_enable",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse", "b200_create_scan_path",
 ]
@@ -106,6 +106,7 @@ def load():
     L.b200_case_get_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_set_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_melt_pool_dimensions.argtypes = [vp, C.c_int32, dp, C.c_double, dp]
+    L.b200_case_isotherm_depth.argtypes = [vp, C.c_int32, dp, dp]
     L.b200_case_solidification_enable.argtypes = [vp, dp, dp, C.c_double, C.c_int64]
     L.b200_case_solidification_events.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.b200_selftest_division.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
@@ -344,6 +345,12 @@ class Case:
         out = np.empty(3 * len(iso))
         _check(self.L.b200_case_melt_pool_dimensions(self.h, len(iso), _P(iso), float(angle_deg), _P(out)))
         return out.reshape(-1, 3)
+
+    def isotherm_depth(self, beam, position):
+        """heatSourceModel::updateDimensions of beam `beam` on the resident T with the beam centre at `position` (collective)."""
+        pos, out = _f64(position), np.zeros(3)
+        _check(self.L.b200_case_isotherm_depth(self.h, beam, _P(pos), _P(out)))
+        return out
 
     def solidification_enable(self, box_min, box_max, iso_value, max_events=1 << 20):
         """solidificationData function object (solidificationData.C): record cooling events on the device from the next step on."""

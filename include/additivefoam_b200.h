@@ -264,6 +264,10 @@ int  b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* is
  * step appends {x, y, z, t, |R|, max(G, small), |R|/G} to a device buffer of maxEvents rows; G = mag(fvc::grad(T)) ("Gauss
  * linear"), R the cooling rate kept from the previous execute, as in the reference.  Per rank, like the reference's
  * data_<proc>.csv (:189-222). */
+/* heatSourceModel::updateDimensions (heatSourceModel.C:123-219) of beam `beam` evaluated on the resident T with the beam centre at
+ * `position`: the dimensions a transient beam would take (x, y static; z the deepest isoValue crossing within the search
+ * radius, never less than the static depth).  The beam's own state is not changed.  Collective over the ranks of the case. */
+int  b200_case_isotherm_depth(b200_case* c, int32_t beam, const double position[3], double dimensions[3]);
 int  b200_case_solidification_enable(b200_case* c, const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents);
 /* Copies this rank's events, in the reference's append order (time step, then cell), into events[maxEvents][7] (may be NULL to
  * query).  *nRecorded = events seen so far; a value above the capacity given at enable means the excess was dropped. */

@@ -70,6 +70,35 @@ def test_gpu_qdot_matches_the_reference_code(ctx, i):
     assert absorbed == pytest.approx(g["eta"] * g["power"], rel=1e-14)
 
 
+def depth_beam(g):
+    if g["kind"] == "modified":
+        return cases.modified_super_gaussian_beam(PATH, dims=g["dims"], k=g["k"], m=g["m"], transient=1, isoValue=g["isoValue"])
+    return cases.projected_gaussian_beam(PATH, dims=g["dims"], A=g["A"], B=g["B"], transient=1, isoValue=g["isoValue"])
+
+
+def depth_case(g, b):
+    case = cases.amb2018_02_b(n=tuple(g["n"]))
+    case["mesh"]["min"], case["mesh"]["max"], case["beams"] = g["min"], g["max"], [b]
+    return case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(DEPTH)))
+def test_gpu_isotherm_depth_matches_the_reference_code(ctx, i):
+    """k_isotherm_depth through b200_case_isotherm_depth against the reference's updateDimensions()."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_ref_qdot_golden as mk
+    g = DEPTH[i]
+    c = lib.Case(ctx, depth_case(g, depth_beam(g)))
+    c.set_field(abi.FIELD_T, np.array(mk.hot_spot(g["n"], g["min"], g["max"], (g["spot"][0], g["spot"][1], g["spot"][2]))))
+    got = c.isotherm_depth(0, g["position"])
+    c.close()
+    want = [float.fromhex(v) for v in g["dimensions"]]
+    # cell centres are origin + (i + 0.5) d on both sides; the interpolation is the same expression
+    assert got[0] == want[0] and got[1] == want[1] and got[2] == pytest.approx(want[2], rel=1e-14)
+
+
 @pytest.mark.parametrize("i", range(len(DEPTH)))
 def test_oracle_isotherm_depth_matches_the_reference_code(oracle, i):
     """heatSourceModel::updateDimensions (heatSourceModel.C:123-219) as the reference's own code runs it on a hot-spot temperature
@@ -83,8 +112,7 @@ def test_oracle_isotherm_depth_matches_the_reference_code(oracle, i):
         b = cases.modified_super_gaussian_beam(PATH, dims=g["dims"], k=g["k"], m=g["m"], transient=1, isoValue=g["isoValue"])
     else:
         b = cases.projected_gaussian_beam(PATH, dims=g["dims"], A=g["A"], B=g["B"], transient=1, isoValue=g["isoValue"])
-    case = cases.amb2018_02_b(n=tuple(g["n"]))
-    case["mesh"]["min"], case["mesh"]["max"], case["beams"] = g["min"], g["max"], [b]
+    case = depth_case(g, b)
     o = ol.OracleCase(case, lib=oracle)
     o.set_field(abi.FIELD_T, np.array(mk.hot_spot(g["n"], g["min"], g["max"], (g["spot"][0], g["spot"][1], g["spot"][2]))))
     pos, dims = np.array(g["position"]), np.zeros(3)
