@@ -80,3 +80,65 @@ def test_rosenthal_analytic_gpu(ctx):
         r = g.step()
     rosenthal.check(rosenthal.compare(g.field(abi.FIELD_T), r.time, case["mesh"]))
     g.close()
+
+
+def test_multibeam_50m_power_and_bounds(ctx):
+    """configs[3]: tutorials/multiBeam's two beam types on four simultaneous tracks, 1000x250x200 = 50 M cells, implicit PCG/DIC.
+    sum(V*qDot) = sum_i eta_i(aspectRatio_i) P_i every step: constant absorption for the superGaussian pair, Kelly (cone) for
+    the transient modifiedSuperGaussian pair, whose aspect ratio is the static one until a 1620 K isotherm exists and can only
+    grow after that (heatSourceModel.C:249-257, :214-218)."""
+    case = cases.multi_beam(n=(1000, 250, 200), deltaT=1e-5)
+    g = lib.Case(ctx, case)
+    kelly = case["beams"][1]
+    eta_static = lib.beam_absorption_eta(kelly, 30e-6 / 40e-6)
+    assert eta_static == 0.35                                      # aspect ratio <= 1: etaMin (KellyAbsorption.C:67-71)
+    t = 0.0
+    for s in range(15):
+        r = g.step()
+        t += r.deltaT
+        assert r.time == pytest.approx(t, rel=1e-12)
+        lo = 2 * 0.33 * 179.2 + 2 * eta_static * 179.2
+        hi = 2 * 0.33 * 179.2 + 2 * 1.0 * 179.2
+        if s == 0:
+            assert r.totalPower == pytest.approx(lo, rel=1e-11)      # T = 300 K everywhere: static depth
+        assert lo * (1 - 1e-11) <= r.totalPower <= hi
+        assert 1 <= r.nThermoCorr <= 20
+    a, T = g.field(abi.FIELD_ALPHA_SOLID), g.field(abi.FIELD_T)
+    g.close()
+    assert np.isfinite(T).all() and T.min() > 299.999 and T.max() > 1620.0
+    assert a.min() >= 0.0 and a.max() <= 1.0 and a.min() < 0.5
+    # all four tracks are heated; the block's y edges, 2.3 mm away, are untouched
+    nx, ny, nz = 1000, 250, 200
+    top = a.reshape(nz, ny, nx)[-1]
+    Ttop = T.reshape(nz, ny, nx)[-1]
+    for y in (50e-6, -50e-6, 150e-6, -150e-6):
+        j = int((y + 0.5 * ny * 20e-6) / 20e-6)
+        assert Ttop[j].max() > 1000.0                                # every track is being heated
+    assert top[0].min() == 1.0 and top[-1].min() == 1.0
+
+
+def test_multilayer_25m_slab_powder_and_walls(ctx):
+    """configs[4] at the per-GPU share of the 8-GPU run (200 M / 8 = 25 M cells: 1000x500x50): powder layer above z = -40 um,
+    fixedValue 300 K bottom and sides, transient Kelly modifiedSuperGaussian on a raster path.  Properties: absorbed power within
+    the Kelly bounds and exactly etaMin*P on the cold first step, powder only ever removed, and removed wherever the cell was
+    not fully solid at the start of a step (updateProperties.H:7-10), temperatures finite and not below the wall value (to the
+    solver tolerance)."""
+    case = cases.multi_layer_pbf(n=(1000, 500, 50), deltaT=1e-5)
+    g = lib.Case(ctx, case)
+    p0 = g.field(abi.FIELD_ALPHA_POWDER)
+    assert set(np.unique(p0)) == {0.0, 1.0}
+    for s in range(15):
+        if s == 14:
+            a4 = g.field(abi.FIELD_ALPHA_SOLID)                      # what the last step's updateProperties sees
+        r = g.step()
+        if s == 0:
+            assert r.totalPower == pytest.approx(0.35 * 195.0, rel=1e-11)
+        assert 0.35 * 195.0 * (1 - 1e-11) <= r.totalPower <= 195.0
+    p, a, T = g.field(abi.FIELD_ALPHA_POWDER), g.field(abi.FIELD_ALPHA_SOLID), g.field(abi.FIELD_T)
+    g.close()
+    assert np.isfinite(T).all() and T.min() >= 300.0 - 1e-6 and T.max() > 1620.0
+    assert np.all(p <= p0) and set(np.unique(p)) <= {0.0, 1.0}
+    molten = a4 < 1.0
+    assert molten.any() and not p[molten].any()
+    assert (p0 - p).sum() >= (molten & (p0 == 1.0)).sum() > 0
+    assert a.min() >= 0.0 and a.max() <= 1.0
