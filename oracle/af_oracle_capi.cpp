@@ -295,4 +295,19 @@ int afo_case_isotherm_depth(void* h, int b, const scalar position[3], scalar dim
     return 0;
 }
 
+// Test probe for the multi-beam heat source: what setDeltaT.H:47-49 and additiveFoam.C:74-76 do with the sources, nothing else --
+// movingHeatSourceModel::adjustDeltaT (movingHeatSourceModel.C:92-98) on the proposed deltaT, ::update (:100-150) over
+// [time, time + deltaT], then time += deltaT.  *dtOut = the adjusted deltaT; qDot is read with afo_case_get_field.
+int afo_case_sources_probe(void* h, scalar proposedDeltaT, scalar* dtOut)
+{
+    Case* c = (Case*)h;
+    scalar dt = proposedDeltaT;
+    for (HeatSource& hs : c->sources) hs.beam.adjustDeltaT(dt, c->time);
+    c->deltaT = dt;
+    c->updateSources();
+    c->time += dt;
+    *dtOut = dt;
+    return 0;
+}
+
 } // extern "C"

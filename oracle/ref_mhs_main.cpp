@@ -1,0 +1,94 @@
+// Driver around the REFERENCE's own multi-beam heat source, compiled where it lies:
+//   movingHeatSource/movingHeatSourceModel/movingHeatSourceModel.C   constructor (:34-83), adjustDeltaT (:92-98), update (:100-150:
+//                                                                    sub-cycling each beam over the time step, time-weighted mean)
+//   movingHeatSource/heatSourceModels/heatSourceModel/heatSourceModel.C, the three shape sources      (as in ref_qdot_main.cpp)
+//   movingHeatSource/movingBeam/movingBeam.C, movingHeatSource/segment/segment.C                      (ref_mhs_beam.cpp)
+// against the REAL movingHeatSourceModel.H / heatSourceModel.H and the stand-ins of oracle/ref_stubs/hsm.  Stand-ins written
+// here: heatSourceModel::New (run-time selection by the source's `heatSourceModel` entry, heatSourceModelNew.C:33-64) and a
+// constant absorptionModel per source (Kelly is pinned by refKelly).  Request on stdin:
+//   mhs nx ny nz minX minY minZ maxX maxY maxZ  startTime endTime  nBeams nSteps
+//   per beam:  name <super|modified|projected> k m A B  dimX dimY dimZ  nPx nPy nPz  eta  beamDeltaT hitPathIntervals pathFile
+//   per step:  proposedDeltaT
+// Per step it does what setDeltaT.H:47-49 and additiveFoam.C:74-76 do with the sources: adjustDeltaT(deltaT), setDeltaT,
+// update(), runTime++; and prints "dt <hex>", "n <nonzero cells>", then "<cell> <hex qDot>" rows.
+// Built by oracle/Makefile into oracle/_ref/refMHS when /root/reference is present.  TEST INFRASTRUCTURE ONLY: it produces
+// tests/golden/ref_mhs.json (tests/golden/make_ref_mhs_golden.py).
+#include "movingHeatSourceModel.C"
+#include "heatSourceModel.C"
+#include "superGaussian.C"
+#include "modifiedSuperGaussian.C"
+#include "projectedGaussian.C"
+
+#include <iostream>
+
+extern "C" void* refbeam_new(const char* pathFile, double deltaT, int hitPathIntervals, double startTime, double endTime);
+
+namespace Foam
+{
+static std::map<std::string, movingBeam*> theBeams;
+static std::map<std::string, absorptionModel*> theAbsorptions;
+autoPtr<movingBeam> movingBeam::New(const word& name, const dictionary&, const Time&) { return autoPtr<movingBeam>(theBeams.at(name)); }
+autoPtr<absorptionModel> absorptionModel::New(const word& name, const dictionary&, const fvMesh&) { return autoPtr<absorptionModel>(theAbsorptions.at(name)); }
+
+autoPtr<heatSourceModel> heatSourceModel::New(const word& sourceName, const dictionary& dict, const fvMesh& mesh)
+{
+    word modelType("unselected");
+    dictionary sourceDict(dict.optionalSubDict(sourceName));
+    sourceDict.lookup("heatSourceModel") >> modelType;
+    if (modelType == "superGaussian") return autoPtr<heatSourceModel>(new heatSourceModels::superGaussian(sourceName, dict, mesh));
+    if (modelType == "modifiedSuperGaussian") return autoPtr<heatSourceModel>(new heatSourceModels::modifiedSuperGaussian(sourceName, dict, mesh));
+    if (modelType == "projectedGaussian") return autoPtr<heatSourceModel>(new heatSourceModels::projectedGaussian(sourceName, dict, mesh));
+    std::abort();
+}
+}
+#include "hexBlock.H"
+
+int main()
+{
+    using namespace Foam;
+    std::string what;
+    while (std::cin >> what) {
+        if (what != "mhs") return 2;
+        int nx, ny, nz, nBeams, nSteps;
+        double lox, loy, loz, hix, hiy, hiz, startTime, endTime;
+        std::cin >> nx >> ny >> nz >> lox >> loy >> loz >> hix >> hiy >> hiz >> startTime >> endTime >> nBeams >> nSteps;
+        refEntries().clear(); theBeams.clear(); theAbsorptions.clear();
+        std::string names;
+        for (int b = 0; b < nBeams; b++) {
+            std::string name, kind, k, m, A, B, dx, dy, dz, npx, npy, npz, file;
+            double eta, beamDt; int hit;
+            std::cin >> name >> kind >> k >> m >> A >> B >> dx >> dy >> dz >> npx >> npy >> npz >> eta >> beamDt >> hit >> file;
+            const std::string type = kind == "super" ? "superGaussian" : kind == "modified" ? "modifiedSuperGaussian" : "projectedGaussian";
+            const std::string p = name + ".", c = name + "." + type + "Coeffs.";
+            refEntries()[p + "heatSourceModel"] = type;
+            refEntries()[c + "k"] = k; refEntries()[c + "m"] = m; refEntries()[c + "A"] = A; refEntries()[c + "B"] = B;
+            refEntries()[c + "dimensions"] = dx + " " + dy + " " + dz;
+            refEntries()[c + "nPoints"] = npx + " " + npy + " " + npz;
+            theBeams[name] = new movingBeam(refbeam_new(file.c_str(), beamDt, hit, startTime, endTime));
+            theAbsorptions[name] = new absorptionModel;
+            theAbsorptions[name]->eta_ = eta;
+            names += (b ? " " : "") + name;
+        }
+        refEntries()["sources"] = names;
+        fvMesh mesh;
+        mesh.build(nx, ny, nz, vector(lox, loy, loz), vector(hix, hiy, hiz));
+        theMesh = &mesh;
+        mesh.time_.now = startTime;
+        movingHeatSourceModel sources(mesh);
+        for (int s = 0; s < nSteps; s++) {
+            double dt;
+            std::cin >> dt;
+            for (auto& kv : theBeams) refbeam_set_time(kv.second->handle(), mesh.time_.now);
+            sources.adjustDeltaT(dt);                     // setDeltaT.H:47
+            mesh.time_.dt = dt;                           // setDeltaT.H:49
+            sources.update();                             // additiveFoam.C:74
+            mesh.time_.now += dt;                         // additiveFoam.C:76
+            const volScalarField& q = sources.qDot();
+            int n = 0;
+            forAll(q, i) if (q[i] != 0.0) n++;
+            std::printf("dt %a\nn %d\n", dt, n);
+            forAll(q, i) if (q[i] != 0.0) std::printf("%d %a\n", i, q[i]);
+        }
+    }
+    return 0;
+}

@@ -23,39 +23,8 @@ static absorptionModel theAbsorption;
 autoPtr<movingBeam> movingBeam::New(const word&, const dictionary&, const Time&) { return autoPtr<movingBeam>(&theBeam); }
 autoPtr<absorptionModel> absorptionModel::New(const word&, const dictionary&, const fvMesh&) { return autoPtr<absorptionModel>(&theAbsorption); }
 
-// [UPSTREAM] blockMesh for one uniform block: points min + i*d (x fastest), cells x fastest, hex cell -> its 8 points,
-// internal faces in upper-triangular order (per cell: +x, +y, +z neighbours)
-void fvMesh::build(label NX, label NY, label NZ, const vector& lo, const vector& hi)
-{
-    nx = NX; ny = NY; nz = NZ;
-    const vector d((hi.x() - lo.x()) / NX, (hi.y() - lo.y()) / NY, (hi.z() - lo.z()) / NZ);
-    for (label k = 0; k <= NZ; k++) for (label j = 0; j <= NY; j++) for (label i = 0; i <= NX; i++)
-        points_.push_back(point(lo.x() + i * d.x(), lo.y() + j * d.y(), lo.z() + k * d.z()));
-    auto pid = [&](label i, label j, label k) { return i + (NX + 1) * (j + (NY + 1) * k); };
-    static volVectorField cc;
-    cc.clear();
-    for (label k = 0; k < NZ; k++) for (label j = 0; j < NY; j++) for (label i = 0; i < NX; i++) {
-        labelList v;
-        for (label c = 0; c < 8; c++) v.push_back(pid(i + (c & 1), j + ((c >> 1) & 1), k + ((c >> 2) & 1)));
-        cellPoints_.push_back(v);
-        V_.push_back(d.x() * d.y() * d.z());
-        const vector centre(lo.x() + (i + 0.5) * d.x(), lo.y() + (j + 0.5) * d.y(), lo.z() + (k + 0.5) * d.z());
-        cc_.push_back(centre); cc.push_back(centre);
-        const label c0 = i + NX * (j + NY * k);
-        if (i < NX - 1) { owner_.push_back(c0); neighbour_.push_back(c0 + 1); }
-        if (j < NY - 1) { owner_.push_back(c0); neighbour_.push_back(c0 + NX); }
-        if (k < NZ - 1) { owner_.push_back(c0); neighbour_.push_back(c0 + NX * NY); }
-    }
-    C_ = &cc;
 }
-const fvMesh* theMesh = nullptr;
-dimensionedScalar fvc::domainIntegrate(const volScalarField& f)
-{
-    scalar s = 0;
-    forAll(f, i) s += theMesh->V()[i] * f[i];
-    return dimensionedScalar(s);
-}
-}
+#include "hexBlock.H"
 
 int main()
 {

@@ -39,6 +39,7 @@ def load():
     L.afo_case_solidification_events.restype = C.c_int64
     L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     L.afo_case_isotherm_depth.argtypes = [C.c_void_p, C.c_int, dp, dp]
+    L.afo_case_sources_probe.argtypes = [C.c_void_p, C.c_double, dp]
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
         getattr(L, f).restype = C.c_double
         getattr(L, f).argtypes = [C.c_void_p]
@@ -99,6 +100,12 @@ class OracleCase:
     def set_field(self, f, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         assert self.L.afo_case_set_field(self.h, f, P(a)) == 0
+
+    def sources_probe(self, proposed_dt):
+        """adjustDeltaT + update of the sources over [time, time + dt], time += dt; returns the adjusted dt (qDot: field(FIELD_QDOT))."""
+        dt = C.c_double(0.0)
+        assert self.L.afo_case_sources_probe(self.h, float(proposed_dt), C.byref(dt)) == 0
+        return dt.value
 
     def melt_pool_dimensions(self, iso_values, angle_deg=0.0):
         iso = np.ascontiguousarray(iso_values, dtype=np.float64)
