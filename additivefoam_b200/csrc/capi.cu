@@ -356,6 +356,14 @@ int b200_case_isotherm_depth(b200_case* c, int32_t beam, const double position[3
     c->p->isothermDepthProbe(beam, position, dimensions);
     B200_CATCH
 }
+int b200_case_sources_update(b200_case* c, double proposedDeltaT, double* deltaT)
+{
+    B200_TRY
+    B200_CHECK(c && deltaT && proposedDeltaT > 0, "sources_update: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->sourcesUpdate(proposedDeltaT, deltaT);
+    B200_CATCH
+}
 int b200_case_solidification_enable(b200_case* c, const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents)
 {
     B200_TRY

@@ -427,6 +427,19 @@ void ThermalCase::updateSources()
     }
 }
 
+// The sources' share of one pass of the time loop and nothing else: movingHeatSourceModel::adjustDeltaT (movingHeatSourceModel.C:92-98)
+// on the proposed deltaT (setDeltaT.H:47-49), ::update (:100-150) over [time, time + deltaT] (additiveFoam.C:74), then the clock
+// moves on (:76).  qDot is left in FIELD_QDOT; T and the phase fields are untouched.
+void ThermalCase::sourcesUpdate(double proposedDeltaT, double* deltaTOut)
+{
+    double dt = proposedDeltaT;
+    for (auto& hs : sources) hs.beam.adjustDeltaT(dt, time_);
+    deltaT_ = dt;
+    updateSources();
+    time_ += dt;
+    *deltaTOut = dt;
+}
+
 // mixedTemperature::updateCoeffs for every mixed side whose patch is not `updated`, plus (implicit form)
 // the laplacian boundary coefficients of all sides
 void ThermalCase::updateCoeffsT()

@@ -57,6 +57,7 @@ public:
     void getField(int field, double* out);
     void setField(int field, const double* in);
     void isothermDepthProbe(int beam, const double position[3], double dimensionsOut[3]);
+    void sourcesUpdate(double proposedDeltaT, double* deltaTOut);
     void meltPoolDimensions(int nIso, const double* isoValues, double scanPathAngleDeg, double* dims);
     void solidificationEnable(const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents);
     int64_t solidificationEvents(double* out, int64_t maxOut);          // returns the number recorded so far (may exceed capacity)

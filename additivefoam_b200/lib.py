@@ -28,7 +28,7 @@ SYMBOLS = [
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
-    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_solidification_enable",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_sources_update", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse", "b200_create_scan_path",
 ]
@@ -107,6 +107,7 @@ def load():
     L.b200_case_set_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_melt_pool_dimensions.argtypes = [vp, C.c_int32, dp, C.c_double, dp]
     L.b200_case_isotherm_depth.argtypes = [vp, C.c_int32, dp, dp]
+    L.b200_case_sources_update.argtypes = [vp, C.c_double, dp]
     L.b200_case_solidification_enable.argtypes = [vp, dp, dp, C.c_double, C.c_int64]
     L.b200_case_solidification_events.argtypes = [vp, dp, C.c_int64, C.POINTER(C.c_int64)]
     L.b200_selftest_division.argtypes = [vp, C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_int64)]
@@ -351,6 +352,13 @@ class Case:
         pos, out = _f64(position), np.zeros(3)
         _check(self.L.b200_case_isotherm_depth(self.h, beam, _P(pos), _P(out)))
         return out
+
+    def sources_update(self, proposed_dt):
+        """movingHeatSourceModel::adjustDeltaT + ::update over [time, time + dt], then time += dt; returns the adjusted dt.
+        qDot() is field(abi.FIELD_QDOT) (collective)."""
+        dt = C.c_double(0.0)
+        _check(self.L.b200_case_sources_update(self.h, float(proposed_dt), C.cast(C.byref(dt), dp)))
+        return dt.value
 
     def solidification_enable(self, box_min, box_max, iso_value, max_events=1 << 20):
         """solidificationData function object (solidificationData.C): record cooling events on the device from the next step on."""

@@ -268,6 +268,13 @@ int  b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* is
  * `position`: the dimensions a transient beam would take (x, y static; z the deepest isoValue crossing within the search
  * radius, never less than the static depth).  The beam's own state is not changed.  Collective over the ranks of the case. */
 int  b200_case_isotherm_depth(b200_case* c, int32_t beam, const double position[3], double dimensions[3]);
+/* The public interface of the reference's movingHeatSourceModel (movingHeatSourceModel.H:84-94) on the resident case, for a host
+ * that keeps its own time loop: adjustDeltaT(deltaT) over all beams (movingHeatSourceModel.C:92-98; *deltaT = the adjusted
+ * value, as setDeltaT.H:47-49 then hands to runTime), update() over [time, time + *deltaT] (:100-150: every active beam
+ * sub-cycled with its own deltaT, dt-weighted mean, summed), after which the case's clock advances by *deltaT
+ * (additiveFoam.C:74-76).  qDot() is then b200_case_get_field(FIELD_QDOT).  T and the phase fields are not touched.
+ * Collective over the ranks of the case. */
+int  b200_case_sources_update(b200_case* c, double proposedDeltaT, double* deltaT);
 int  b200_case_solidification_enable(b200_case* c, const double boxMin[3], const double boxMax[3], double isoValue, int64_t maxEvents);
 /* Copies this rank's events, in the reference's append order (time step, then cell), into events[maxEvents][7] (may be NULL to
  * query).  *nRecorded = events seen so far; a value above the capacity given at enable means the excess was dropped. */

@@ -3,7 +3,8 @@ code (tests/golden/ref_mhs.json, made by tests/golden/make_ref_mhs_golden.py fro
 movingHeatSourceModel.C with its real header on top of its heatSourceModel.C, shapes, movingBeam.C and segment.C, compiled where
 they lie): every beam sub-cycled over the time step with its own deltaT (ragged last sub-step), dt-weighted mean, sum over
 beams, the time step cut at path intervals, beams that dwell unpowered or have run out.  Checked: the oracle's restatement
-(Case::updateSources + movingBeam::adjustDeltaT), which the GPU stepper is held to in the case tests."""
+(Case::updateSources + movingBeam::adjustDeltaT) and the library (b200_case_sources_update: host movingBeam, k_qdot_weights,
+k_qdot_apply, the sub-cycle accumulation on the device)."""
 import json
 import os
 
@@ -11,7 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as ol
-from additivefoam_b200 import abi, cases
+from additivefoam_b200 import abi, cases, lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = json.load(open(os.path.join(HERE, "golden", "ref_mhs.json")))
@@ -29,13 +30,36 @@ def beam_of(b):
     return d
 
 
-@pytest.mark.parametrize("i", range(len(GOLD)))
-def test_oracle_sources_update_matches_the_reference_code(oracle, i):
-    g = GOLD[i]
+def case_of(g):
     case = cases.amb2018_02_b(n=tuple(g["mesh"]["n"]), startTime=g["start"], endTime=g["end"])
     case["mesh"]["min"], case["mesh"]["max"] = g["mesh"]["min"], g["mesh"]["max"]
     case["beams"] = [beam_of(b) for b in g["beams"]]
-    o = ol.OracleCase(case, lib=oracle)
+    return case
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(len(GOLD)))
+def test_gpu_sources_update_matches_the_reference_code(ctx, i):
+    g = GOLD[i]
+    c = lib.Case(ctx, case_of(g))
+    n = int(np.prod(g["mesh"]["n"]))
+    for s, (proposed, want) in enumerate(zip(g["proposed"], g["steps"])):
+        dt = c.sources_update(proposed)
+        assert dt == float.fromhex(want["dt"]), f"step {s}: adjusted deltaT"        # host arithmetic: bit for bit
+        got = c.field(abi.FIELD_QDOT)
+        ref = np.zeros(n)
+        ref[want["cells"]] = [float.fromhex(v) for v in want["qDot"]]
+        assert np.array_equal(got != 0.0, ref != 0.0), f"step {s}: cells touched"
+        scale = max(np.max(np.abs(ref)), 1e-300)
+        # exp/pow of the device differ from glibc's by <= 1 ulp
+        assert np.max(np.abs(got - ref)) <= 1e-11 * scale, f"step {s}: {np.max(np.abs(got - ref)) / scale}"
+    c.close()
+
+
+@pytest.mark.parametrize("i", range(len(GOLD)))
+def test_oracle_sources_update_matches_the_reference_code(oracle, i):
+    g = GOLD[i]
+    o = ol.OracleCase(case_of(g), lib=oracle)
     n = int(np.prod(g["mesh"]["n"]))
     for s, (proposed, want) in enumerate(zip(g["proposed"], g["steps"])):
         dt = o.sources_probe(proposed)
