@@ -300,6 +300,13 @@ int b200_beam_absorption_eta(const b200_beam* beam, double aspectRatio, double* 
     *eta = heatSourceModel(b, 0.0, 0.0).eta(aspectRatio);
     B200_CATCH
 }
+int b200_mixed_temperature_value_fraction(double h, double emissivity, double Tinf, double Tp, double kappa, double deltaCoeff, double* valueFraction)
+{
+    B200_TRY
+    B200_CHECK(valueFraction != nullptr, "null argument");
+    *valueFraction = mixed_value_fraction(h, emissivity, Tinf, Tp, kappa, deltaCoeff);
+    B200_CATCH
+}
 
 int b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out)
 {

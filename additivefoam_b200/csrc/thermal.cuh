@@ -13,6 +13,16 @@
 #include <memory>
 
 namespace b200 {
+// mixedTemperatureFvPatchScalarField::updateCoeffs (derivedFvPatchFields/mixedTemperature/mixedTemperatureFvPatchScalarField.C:157-188):
+// the value fraction of one face; refValue = Tinf, refGrad = 0.  Same expression on the host (b200_mixed_temperature_value_fraction,
+// checked against the reference's source) and in k_side_coeffs.
+__host__ __device__ inline double mixed_value_fraction(double h, double emissivity, double Tinf, double Tp, double kappa, double deltaCoeff)
+{
+    const double sigma = 5.67e-8;
+    const double hEff = h + sigma * emissivity * (Tp * Tp + Tinf * Tinf) * (Tp + Tinf);
+    return 1.0 / (1.0 + kappa * deltaCoeff / fmax(hEff, 1e-15));
+}
+
 
 struct Geom {
     double ox, oy, oz, dx, dy, dz, V;

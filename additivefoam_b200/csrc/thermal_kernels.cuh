@@ -157,9 +157,7 @@ __global__ void k_side_coeffs(BlockDims d, Geom g, int s, int type, double fixed
         double f = 0.0;
         if (type == B200_BC_MIXED_TEMPERATURE) {
             if (doUpdateCoeffs) {
-                const double Tp = Tb[q], sigma = 5.67e-8;
-                const double hEff = h + sigma * emissivity * (Tp * Tp + Tinf * Tinf) * (Tp + Tinf);
-                f = 1.0 / (1.0 + kappa[c] * delta / fmax(hEff, 1e-15));
+                f = mixed_value_fraction(h, emissivity, Tinf, Tb[q], kappa[c], delta);
                 valueFraction[q] = f;
             } else f = valueFraction[q];
         }

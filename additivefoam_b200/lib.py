@@ -27,7 +27,7 @@ SYMBOLS = [
     "b200_ctx_peer_export", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
-    "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
+    "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_mixed_temperature_value_fraction", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
     "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_sources_update", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse", "b200_create_scan_path",
@@ -98,6 +98,7 @@ def load():
     L.b200_beam_shape_v0.argtypes = [C.POINTER(abi.Beam), dp, dp, dp]
     L.b200_beam_shape_weight.argtypes = [C.POINTER(abi.Beam), dp, dp, dp]
     L.b200_beam_absorption_eta.argtypes = [C.POINTER(abi.Beam), C.c_double, dp]
+    L.b200_mixed_temperature_value_fraction.argtypes = [C.c_double] * 6 + [dp]
     L.b200_case_create.argtypes = [vp, C.POINTER(abi.CaseDesc), C.POINTER(vp)]
     L.b200_case_destroy.argtypes = [vp]
     L.b200_case_running.argtypes = [vp]
@@ -431,3 +432,10 @@ def scan_path_parse(text, max_segments=4096):
     if n < 0:
         raise B200Error("scan path has more segments than max_segments")
     return out[: 6 * n].reshape(n, 6).copy()
+
+
+def mixed_temperature_value_fraction(h, emissivity, Tinf, Tp, kappa, delta_coeff):
+    """mixedTemperatureFvPatchScalarField::updateCoeffs: the value fraction of one face (host only)."""
+    f = C.c_double(0.0)
+    _check(load().b200_mixed_temperature_value_fraction(h, emissivity, Tinf, Tp, kappa, delta_coeff, C.cast(C.byref(f), dp)))
+    return f.value

@@ -242,6 +242,12 @@ int  b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam*
 int  b200_beam_shape_v0(const b200_beam* beam, const double dimensions[3], double* V0, double* kResolved);
 int  b200_beam_shape_weight(const b200_beam* beam, const double dimensions[3], const double d[3], double* weight);
 int  b200_beam_absorption_eta(const b200_beam* beam, double aspectRatio, double* eta);
+/* Host mirror of the top-surface boundary condition (no device, no context): the value fraction
+ * mixedTemperatureFvPatchScalarField::updateCoeffs (derivedFvPatchFields/mixedTemperature/mixedTemperatureFvPatchScalarField.C:
+ * 157-188) assigns to a face with patch temperature Tp, patch conductivity kappa and deltaCoeffs deltaCoeff (refValue = Tinf,
+ * refGradient = 0).  The same function is what the device kernel evaluates. */
+int  b200_mixed_temperature_value_fraction(double h, double emissivity, double Tinf, double Tp, double kappa, double deltaCoeff,
+                                           double* valueFraction);
 
 /* ---- The GPU-resident thermal step (everything in SURVEY section 3.2 items 1,3,4,6,8). */
 int  b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out);

@@ -295,6 +295,10 @@ int afo_case_isotherm_depth(void* h, int b, const scalar position[3], scalar dim
     return 0;
 }
 
+scalar afo_mixed_value_fraction(scalar h, scalar emissivity, scalar Tinf, scalar Tp, scalar kap, scalar deltaCoeff)
+{
+    return mixedValueFraction(h, emissivity, Tinf, Tp, kap, deltaCoeff);
+}
 // Test probe for the multi-beam heat source: what setDeltaT.H:47-49 and additiveFoam.C:74-76 do with the sources, nothing else --
 // movingHeatSourceModel::adjustDeltaT (movingHeatSourceModel.C:92-98) on the proposed deltaT, ::update (:100-150) over
 // [time, time + deltaT], then time += deltaT.  *dtOut = the adjusted deltaT; qDot is read with afo_case_get_field.

@@ -300,6 +300,12 @@ inline void Case::updateProperties()
 }
 
 // mixedTemperatureFvPatchScalarField.C:157-188 (updateCoeffs) for every T patch of rank r
+inline scalar mixedValueFraction(scalar h, scalar emissivity, scalar Tinf, scalar Tp, scalar kap, scalar deltaCoeff)
+{
+    const scalar sigma = 5.67e-8;
+    const scalar hEff = h + sigma * emissivity * (Tp * Tp + Tinf * Tinf) * (Tp + Tinf);
+    return 1.0 / (1.0 + kap * deltaCoeff / std::max(hEff, 1e-15));
+}
 inline void Case::updateCoeffsT(int r)
 {
     RankState& s = rk[r];
@@ -309,8 +315,8 @@ inline void Case::updateCoeffsT(int r)
         for (size_t i = 0; i < p.faceCells.size(); i++) {
             const scalar Tp = p.Tb[i];
             const scalar kap = s.kappa[p.faceCells[i]];                 // zeroGradient kappa patch value
-            const scalar hEff = p.h + sigma * p.emissivity * (Tp * Tp + p.Tinf * p.Tinf) * (Tp + p.Tinf);
-            p.valueFraction[i] = 1.0 / (1.0 + kap * p.deltaCoeffs[i] / std::max(hEff, 1e-15));
+            (void)sigma;
+            p.valueFraction[i] = mixedValueFraction(p.h, p.emissivity, p.Tinf, Tp, kap, p.deltaCoeffs[i]);
         }
         p.updated = true;
     }

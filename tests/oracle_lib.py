@@ -40,6 +40,8 @@ def load():
     L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     L.afo_case_isotherm_depth.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.afo_case_sources_probe.argtypes = [C.c_void_p, C.c_double, dp]
+    L.afo_mixed_value_fraction.restype = C.c_double
+    L.afo_mixed_value_fraction.argtypes = [C.c_double] * 6
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
         getattr(L, f).restype = C.c_double
         getattr(L, f).argtypes = [C.c_void_p]
