@@ -295,6 +295,16 @@ int afo_case_isotherm_depth(void* h, int b, const scalar position[3], scalar dim
     return 0;
 }
 
+// Test probe: the state the control fragments of the NEXT step will see -- updateProperties() (additiveFoam.C:68; idempotent, the
+// step repeats it) so that kappa and Cp are current, and T.oldTime().  Single-rank cases only.
+int afo_case_pre_step_state(void* h, scalar* Told)
+{
+    Case* c = (Case*)h;
+    if (c->R != 1) return 1;
+    c->updateProperties();
+    std::copy(c->rk[0].Told.begin(), c->rk[0].Told.end(), Told);
+    return 0;
+}
 scalar afo_mixed_value_fraction(scalar h, scalar emissivity, scalar Tinf, scalar Tp, scalar kap, scalar deltaCoeff)
 {
     return mixedValueFraction(h, emissivity, Tinf, Tp, kap, deltaCoeff);

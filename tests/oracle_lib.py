@@ -40,6 +40,7 @@ def load():
     L.afo_case_assemble_probe.argtypes = [C.c_void_p, C.c_int, dp, dp, dp]
     L.afo_case_isotherm_depth.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.afo_case_sources_probe.argtypes = [C.c_void_p, C.c_double, dp]
+    L.afo_case_pre_step_state.argtypes = [C.c_void_p, dp]
     L.afo_mixed_value_fraction.restype = C.c_double
     L.afo_mixed_value_fraction.argtypes = [C.c_double] * 6
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
@@ -102,6 +103,12 @@ class OracleCase:
     def set_field(self, f, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         assert self.L.afo_case_set_field(self.h, f, P(a)) == 0
+
+    def pre_step_state(self):
+        """updateProperties() (so that kappa, Cp are what the next step's controls see) and T.oldTime()."""
+        Told = np.empty(self.n, dtype=np.float64)
+        assert self.L.afo_case_pre_step_state(self.h, P(Told)) == 0
+        return Told
 
     def sources_probe(self, proposed_dt):
         """adjustDeltaT + update of the sources over [time, time + dt], time += dt; returns the adjusted dt (qDot: field(FIELD_QDOT))."""
