@@ -1,9 +1,13 @@
 // TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT PATH.
 // CPU restatement of AdditiveFOAM's moving heat source library
 // (applications/solvers/additiveFoam/movingHeatSource, "MHS/" below): scan path,
-// beam kinematics, absorption models and the three beam shapes.  Parity unpinned (the
-// reference ships no golden vectors; see af_ldu.hpp header); anchored on the derived
-// values of SURVEY.md Appendix B in tests/test_oracle_anchors.py.
+// beam kinematics, absorption models and the three beam shapes.  The reference ships no
+// golden vectors, but this part of it compiles without OpenFOAM: PARITY PINNED on outputs
+// of the reference's own sources built into oracle/_ref (oracle/Makefile) -- movingBeam.C,
+// segment.C (refBeam, bit-exact), KellyAbsorption.C (refKelly, bit-exact), the three shape
+// sources (refModels: V0 <= 2 ulp, weights 1e-13), frozen as tests/golden/ref_*.json and
+// checked by tests/test_ref_beam.py and tests/test_ref_models.py; the derived values of
+// SURVEY.md Appendix B stay as anchors in tests/test_oracle_anchors.py.
 #pragma once
 #include "af_ldu.hpp"
 #include <sstream>

@@ -4,7 +4,16 @@
 // blockMesh hex block, serial or decomposed into z-slabs (the reference's MPI ranks are
 // emulated in-process).  PARITY UNPINNED at the OpenFOAM-10 boundary: fvm::ddt,
 // fvm::laplacian, harmonic interpolation, boundary coefficients and fvMatrix::solve are
-// restated from upstream, not executed.  See af_ldu.hpp header.
+// restated from upstream, not executed (thermoScheme.H and the
+// corrector loop of TEqn.H are operator expressions over them).  See af_ldu.hpp header.
+// PINNED on the reference's own text or sources built into oracle/_ref (oracle/Makefile;
+// fixtures tests/golden/ref_*.json): updateProperties.H and thermoSource.H (verbatim,
+// bit-exact, tests/test_ref_models.py), setDeltaT.H and solutionControls.H (verbatim,
+// bit-exact per step, tests/test_ref_ctl.py), heatSourceModel.C qDot / updateDimensions
+// (tests/test_ref_qdot.py), movingHeatSourceModel.C adjustDeltaT / update
+// (tests/test_ref_mhs.py), mixedTemperatureFvPatchScalarField.C updateCoeffs (bit-exact,
+// tests/test_ref_bc.py), and the function objects meltPoolDimensions.C and
+// solidificationData.C (tests/test_ref_fo.py, tests/test_ref_solid.py).
 #pragma once
 #include "af_beam.hpp"
 #include "../include/additivefoam_b200.h"
