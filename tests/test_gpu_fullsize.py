@@ -142,3 +142,31 @@ def test_multilayer_25m_slab_powder_and_walls(ctx):
     assert molten.any() and not p[molten].any()
     assert (p0 - p).sum() >= (molten & (p0 == 1.0)).sum() > 0
     assert a.min() >= 0.0 and a.max() <= 1.0
+
+
+def test_track_100m_full_size_properties(ctx):
+    """configs[2] at its full size (1000x400x250 = 100 M cells, the workload bench.py times): absorbed power exact, the clock
+    advances by the reported deltaT, every solve ends below its initial residual, alpha.solid stays in [0, 1] and is consistent
+    with T outside the mushy zone, nothing but the track region is heated."""
+    nx, ny, nz = 1000, 400, 250
+    g = lib.Case(ctx, cases.synthetic_track((nx, ny, nz), deltaT=1e-5))
+    t = 0.0
+    for _ in range(10):
+        r = g.step()
+        t += r.deltaT
+        assert r.time == pytest.approx(t, rel=1e-12)
+        assert r.totalPower == pytest.approx(0.33 * 179.2, rel=1e-11)
+        assert r.explicitStep == 0 and 1 <= r.nThermoCorr <= 20
+        assert r.lastFinalResidual <= r.lastInitialResidual and np.isfinite(r.lastFinalResidual)
+    a = np.empty(nx * ny * nz)
+    T = np.empty(nx * ny * nz)
+    g.field_into(abi.FIELD_ALPHA_SOLID, a)
+    g.field_into(abi.FIELD_T, T)
+    g.close()
+    assert np.isfinite(T).all() and T.min() > 299.999 and T.max() > 1620.0
+    assert a.min() >= 0.0 and a.max() <= 1.0 and a.min() < 0.5
+    top = T.reshape(nz, ny, nx)[-1]
+    assert top[ny // 2 - 1:ny // 2 + 1].max() == T.max()                          # hottest on the track line y = 0
+    assert np.all(T.reshape(nz, ny, nx)[: nz // 2] < 300.001)                       # 2.5 mm below the surface: untouched after 100 us
+    hot, cold = T > 1620.0 + 1e-6, T < 1410.0 - 1e-6
+    assert np.all(a[hot] <= 1e-6) and np.all(a[cold] >= 1.0 - 1e-6)
