@@ -5,9 +5,9 @@
 //   movingHeatSource/movingBeam/movingBeam.C, movingHeatSource/segment/segment.C                      (ref_mhs_beam.cpp)
 // against the REAL movingHeatSourceModel.H / heatSourceModel.H and the stand-ins of oracle/ref_stubs/hsm.  Stand-ins written
 // here: heatSourceModel::New (run-time selection by the source's `heatSourceModel` entry, heatSourceModelNew.C:33-64) and a
-// constant absorptionModel per source (Kelly is pinned by refKelly).  Request on stdin:
+// absorptionModel::New (a constant eta, or the reference's own KellyAbsorption.C through ref_mhs_kelly.cpp).  Request on stdin:
 //   mhs nx ny nz minX minY minZ maxX maxY maxZ  startTime endTime  nBeams nSteps
-//   per beam:  name <super|modified|projected> k m A B  dimX dimY dimZ  nPx nPy nPz  eta  beamDeltaT hitPathIntervals pathFile
+//   per beam:  name <super|modified|projected> k m A B  dimX dimY dimZ  nPx nPy nPz  <eta | kelly:<cone|cylinder>:eta0:etaMin>  beamDeltaT hitPathIntervals pathFile
 //   per step:  proposedDeltaT
 // Per step it does what setDeltaT.H:47-49 and additiveFoam.C:74-76 do with the sources: adjustDeltaT(deltaT), setDeltaT,
 // update(), runTime++; and prints "dt <hex>", "n <nonzero cells>", then "<cell> <hex qDot>" rows.
@@ -22,6 +22,7 @@
 #include <iostream>
 
 extern "C" void* refbeam_new(const char* pathFile, double deltaT, int hitPathIntervals, double startTime, double endTime);
+extern "C" void* refkelly_new(const char* geometry, double eta0, double etaMin);
 
 namespace Foam
 {
@@ -56,7 +57,7 @@ int main()
         std::string names;
         for (int b = 0; b < nBeams; b++) {
             std::string name, kind, k, m, A, B, dx, dy, dz, npx, npy, npz, file;
-            double eta, beamDt; int hit;
+            std::string eta; double beamDt; int hit;
             std::cin >> name >> kind >> k >> m >> A >> B >> dx >> dy >> dz >> npx >> npy >> npz >> eta >> beamDt >> hit >> file;
             const std::string type = kind == "super" ? "superGaussian" : kind == "modified" ? "modifiedSuperGaussian" : "projectedGaussian";
             const std::string p = name + ".", c = name + "." + type + "Coeffs.";
@@ -66,7 +67,10 @@ int main()
             refEntries()[c + "nPoints"] = npx + " " + npy + " " + npz;
             theBeams[name] = new movingBeam(refbeam_new(file.c_str(), beamDt, hit, startTime, endTime));
             theAbsorptions[name] = new absorptionModel;
-            theAbsorptions[name]->eta_ = eta;
+            if (eta.rfind("kelly:", 0) == 0) {
+                const size_t a = eta.find(':', 6), b = eta.find(':', a + 1);
+                theAbsorptions[name]->kelly_ = refkelly_new(eta.substr(6, a - 6).c_str(), std::atof(eta.substr(a + 1, b - a - 1).c_str()), std::atof(eta.substr(b + 1).c_str()));
+            } else theAbsorptions[name]->eta_ = std::atof(eta.c_str());
             names += (b ? " " : "") + name;
         }
         refEntries()["sources"] = names;

@@ -22,8 +22,9 @@ RASTER = [[1, 0.0, -1e-4, 0.0, 0.0, 0.0], [0, 4e-4, -1e-4, 0.0, 195.0, 0.8], [1,
 LATE = [[1, 1e-4, -1e-4, 0.0, 0.0, 2e-4], [0, 4e-4, -1e-4, 0.0, 120.0, 0.5]]                   # powered only after a 200 us dwell
 
 
-def beam(name, kind, path, dims, nPoints=(5, 5, 5), k=2.0, m=0.0, A=0.0, B=0.0, eta=0.33, deltaT=0.0, hit=1):
-    return dict(name=name, kind=kind, path=path, dims=list(dims), nPoints=list(nPoints), k=k, m=m, A=A, B=B, eta=eta, deltaT=deltaT, hit=hit)
+def beam(name, kind, path, dims, nPoints=(5, 5, 5), k=2.0, m=0.0, A=0.0, B=0.0, eta=0.33, deltaT=0.0, hit=1, kelly=None):
+    """kelly = (geometry, eta0, etaMin): the reference's own KellyAbsorption.C decides eta from the beam's aspect ratio."""
+    return dict(name=name, kind=kind, path=path, dims=list(dims), nPoints=list(nPoints), k=k, m=m, A=A, B=B, eta=eta, deltaT=deltaT, hit=hit, kelly=kelly)
 
 
 CONFIGS = [
@@ -42,6 +43,11 @@ CONFIGS = [
          steps=[5e-5, 5e-5, 8e-5, 8e-5, 5e-5]),
     # hitPathIntervals off: the step straddles the end of the line; the sub-steps after the beam switches off add nothing
     dict(start=4.6e-4, end=2e-3, beams=[beam("beam1", "super", RASTER, (85e-6, 85e-6, 30e-6), deltaT=6e-6, hit=0)], steps=[6e-5, 6e-5, 9e-5]),
+    # Kelly absorption through qDot(): eta from dimensions.z / min(dimensions.x, dimensions.y) (heatSourceModel.C:249-257) -- a cone of
+    # aspect ratio 2.25, a cylinder whose x and y differ (ratio 2, not 1.2), and a shallow one (ratio < 1: etaMin)
+    dict(start=0.0, end=1e-3, beams=[beam("beam1", "modified", TRACK, (40e-6, 40e-6, 90e-6), k=7.95, m=2.72, deltaT=5e-6, kelly=("cone", 0.28, 0.35)),
+                                     beam("beam2", "super", BACK, (50e-6, 30e-6, 60e-6), k=2.0, kelly=("cylinder", 0.3, 0.2))], steps=[2e-5, 2e-5]),
+    dict(start=0.0, end=1e-3, beams=[beam("beam1", "projected", TRACK, (60e-6, 80e-6, 45e-6), A=2.0, B=1.0, kelly=("cone", 0.28, 0.35))], steps=[1.5e-5, 1.5e-5]),
     # a time step that ends after the whole path: activePath() switches the beam off for the following step
     dict(start=5.9e-4, end=2e-3, beams=[beam("beam1", "super", TRACK, (85e-6, 85e-6, 30e-6), deltaT=1e-5, hit=0)], steps=[3e-5, 3e-5, 3e-5]),
 ]
@@ -60,6 +66,8 @@ def run(cfg, tmp):
             fh.write(path_text(b["path"]))
         lines.append("%s %s %r %r %r %r  %r %r %r  %d %d %d  %r  %r %d %s" % (b["name"], b["kind"], b["k"], b["m"], b["A"], b["B"], *b["dims"], *b["nPoints"],
                                                                              b["eta"], b["deltaT"] if b["deltaT"] > 0 else -1.0, b["hit"], f))
+        if b["kelly"]:
+            lines[-1] = lines[-1].replace("  %r  " % b["eta"], "  kelly:%s:%r:%r  " % tuple(b["kelly"]), 1)
     lines += [repr(dt) for dt in cfg["steps"]]
     out = subprocess.run([REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
     out = [ln for ln in out if ln]

@@ -27,6 +27,10 @@ def beam_of(b):
     else:
         d = cases.projected_gaussian_beam(b["path"], dims=b["dims"], nPoints=b["nPoints"], A=b["A"], B=b["B"], transient=0, eta=b["eta"])
     d["deltaT"], d["hitPathIntervals"] = b["deltaT"], b["hit"]
+    if b.get("kelly"):
+        geometry, eta0, etaMin = b["kelly"]
+        d["absorptionModel"], d["eta0"], d["etaMin"] = abi.ABSORPTION_KELLY, eta0, etaMin
+        d["kellyGeometry"] = abi.KELLY_CONE if geometry == "cone" else abi.KELLY_CYLINDER
     return d
 
 
