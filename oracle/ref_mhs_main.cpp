@@ -1,11 +1,11 @@
 // Driver around the REFERENCE's own multi-beam heat source, compiled where it lies:
 //   movingHeatSource/movingHeatSourceModel/movingHeatSourceModel.C   constructor (:34-83), adjustDeltaT (:92-98), update (:100-150:
 //                                                                    sub-cycling each beam over the time step, time-weighted mean)
-//   movingHeatSource/heatSourceModels/heatSourceModel/heatSourceModel.C, the three shape sources      (as in ref_qdot_main.cpp)
+//   movingHeatSource/heatSourceModels/heatSourceModel/heatSourceModel.C, heatSourceModelNew.C (run-time selection by the source's
+//                                                                    `heatSourceModel` entry against each class's TypeName), the three shape sources
 //   movingHeatSource/movingBeam/movingBeam.C, movingHeatSource/segment/segment.C                      (ref_mhs_beam.cpp)
-// against the REAL movingHeatSourceModel.H / heatSourceModel.H and the stand-ins of oracle/ref_stubs/hsm.  Stand-ins written
-// here: heatSourceModel::New (run-time selection by the source's `heatSourceModel` entry, heatSourceModelNew.C:33-64) and a
-// absorptionModel::New (a constant eta, or the reference's own KellyAbsorption.C through ref_mhs_kelly.cpp).  Request on stdin:
+// against the REAL movingHeatSourceModel.H / heatSourceModel.H and the stand-ins of oracle/ref_stubs/hsm.  Stand-in written
+// here: absorptionModel::New (a constant eta, or the reference's own KellyAbsorption.C through ref_mhs_kelly.cpp).  Request on stdin:
 //   mhs nx ny nz minX minY minZ maxX maxY maxZ  startTime endTime  nBeams nSteps
 //   per beam:  name <super|modified|projected> k m A B  dimX dimY dimZ  nPx nPy nPz  <eta | kelly:<cone|cylinder>:eta0:etaMin>  beamDeltaT hitPathIntervals pathFile
 //   per step:  proposedDeltaT
@@ -15,6 +15,7 @@
 // tests/golden/ref_mhs.json (tests/golden/make_ref_mhs_golden.py).
 #include "movingHeatSourceModel.C"
 #include "heatSourceModel.C"
+#include "heatSourceModelNew.C"
 #include "superGaussian.C"
 #include "modifiedSuperGaussian.C"
 #include "projectedGaussian.C"
@@ -31,16 +32,6 @@ static std::map<std::string, absorptionModel*> theAbsorptions;
 autoPtr<movingBeam> movingBeam::New(const word& name, const dictionary&, const Time&) { return autoPtr<movingBeam>(theBeams.at(name)); }
 autoPtr<absorptionModel> absorptionModel::New(const word& name, const dictionary&, const fvMesh&) { return autoPtr<absorptionModel>(theAbsorptions.at(name)); }
 
-autoPtr<heatSourceModel> heatSourceModel::New(const word& sourceName, const dictionary& dict, const fvMesh& mesh)
-{
-    word modelType("unselected");
-    dictionary sourceDict(dict.optionalSubDict(sourceName));
-    sourceDict.lookup("heatSourceModel") >> modelType;
-    if (modelType == "superGaussian") return autoPtr<heatSourceModel>(new heatSourceModels::superGaussian(sourceName, dict, mesh));
-    if (modelType == "modifiedSuperGaussian") return autoPtr<heatSourceModel>(new heatSourceModels::modifiedSuperGaussian(sourceName, dict, mesh));
-    if (modelType == "projectedGaussian") return autoPtr<heatSourceModel>(new heatSourceModels::projectedGaussian(sourceName, dict, mesh));
-    std::abort();
-}
 }
 #include "hexBlock.H"
 
