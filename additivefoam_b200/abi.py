@@ -14,7 +14,7 @@ XMIN, XMAX, YMIN, YMAX, ZMIN, ZMAX = range(6)
 SUPER_GAUSSIAN, MODIFIED_SUPER_GAUSSIAN, PROJECTED_GAUSSIAN = 0, 1, 2
 ABSORPTION_CONSTANT, ABSORPTION_KELLY = 0, 1
 KELLY_CONE, KELLY_CYLINDER = 0, 1
-FIELD_T, FIELD_ALPHA_SOLID, FIELD_ALPHA_POWDER, FIELD_KAPPA, FIELD_CP, FIELD_QDOT, FIELD_DFDT, FIELD_T0 = range(8)
+FIELD_T, FIELD_ALPHA_SOLID, FIELD_ALPHA_POWDER, FIELD_KAPPA, FIELD_CP, FIELD_QDOT, FIELD_DFDT, FIELD_T0, FIELD_T_OLD, FIELD_ALPHA_SOLID_OLD = range(10)
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

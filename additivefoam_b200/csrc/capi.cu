@@ -57,6 +57,14 @@ int b200_ctx_peer_export(b200_ctx* ctx, void* handle64)
     ctx->p->peerExport(handle64);
     B200_CATCH
 }
+int b200_ctx_peer_export_halo(b200_ctx* ctx, int64_t haloDoubles, void* handle64)
+{
+    B200_TRY
+    B200_CHECK(haloDoubles >= 0, "peer_export_halo: negative window size");
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    ctx->p->peerExport(handle64, (size_t)haloDoubles);
+    B200_CATCH
+}
 int b200_ctx_peer_import(b200_ctx* ctx, const void* handles)
 {
     B200_TRY
@@ -67,6 +75,7 @@ int b200_ctx_peer_import(b200_ctx* ctx, const void* handles)
 int b200_ctx_synchronize(b200_ctx* ctx)
 {
     B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
     ctx->p->sync();
     B200_CATCH
 }
@@ -117,12 +126,13 @@ int b200_ldu_create(b200_ctx* ctx, int32_t nCells, int32_t nFaces, const int32_t
 int b200_ldu_destroy(b200_ldu* ldu)
 {
     B200_TRY
-    if (ldu) { delete ldu->p; delete ldu; }
+    if (ldu) { cudaSetDevice(ldu->p->ctx->device); delete ldu->p; delete ldu; }
     B200_CATCH
 }
 int b200_ldu_set_block(b200_ldu* ldu, int32_t nx, int32_t ny, int32_t nz)
 {
     B200_TRY
+    B200_CUDA(cudaSetDevice(ldu->p->ctx->device));
     ldu->p->setBlock(nx, ny, nz);
     B200_CATCH
 }
@@ -201,6 +211,7 @@ int b200_ldu_amul_dev(b200_ldu* ldu, const double* diag_dev, const double* upper
 {
     B200_TRY
     Ldu& L = *ldu->p;
+    B200_CUDA(cudaSetDevice(L.ctx->device));
     MatrixView A; A.diag = diag_dev; A.upper = upper_dev; A.lower = lower_dev ? lower_dev : upper_dev; A.bouCoeffs = ifaceBouCoeffs_dev;
     L.amul(A, psi_dev, Apsi_dev);
     B200_CATCH
@@ -318,7 +329,7 @@ int b200_case_create(b200_ctx* ctx, const b200_case_desc* desc, b200_case** out)
 int b200_case_destroy(b200_case* c)
 {
     B200_TRY
-    if (c) { delete c->p; delete c; }
+    if (c) { cudaSetDevice(c->p->ctx->device); delete c->p; delete c; }
     B200_CATCH
 }
 int b200_case_running(b200_case* c) { return c->p->running() ? 1 : 0; }
@@ -339,19 +350,52 @@ int b200_case_n_cells(b200_case* c, int64_t* nLocal, int64_t* nGlobal)
 int b200_case_get_field(b200_case* c, int32_t field, double* out)
 {
     B200_TRY
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
     c->p->getField(field, out);
     B200_CATCH
 }
 int b200_case_set_field(b200_case* c, int32_t field, const double* in)
 {
     B200_TRY
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
     c->p->setField(field, in);
+    B200_CATCH
+}
+int b200_case_set_field_async(b200_case* c, int32_t field, const double* pinnedIn)
+{
+    B200_TRY
+    B200_CHECK(c && pinnedIn, "set_field_async: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->setFieldAsync(field, pinnedIn);
+    B200_CATCH
+}
+int b200_case_apply_staged(b200_case* c)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->applyStaged();
+    B200_CATCH
+}
+int b200_case_get_field_async(b200_case* c, int32_t field, double* pinnedOut)
+{
+    B200_TRY
+    B200_CHECK(c && pinnedOut, "get_field_async: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->getFieldAsync(field, pinnedOut);
+    B200_CATCH
+}
+int b200_case_transfers_wait(b200_case* c)
+{
+    B200_TRY
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->transfersWait();
     B200_CATCH
 }
 int b200_case_melt_pool_dimensions(b200_case* c, int32_t nIso, const double* isoValues, double scanPathAngleDeg, double* dims)
 {
     B200_TRY
     B200_CHECK(c && nIso >= 0 && (nIso == 0 || (isoValues && dims)), "melt_pool_dimensions: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
     c->p->meltPoolDimensions(nIso, isoValues, scanPathAngleDeg, dims);
     B200_CATCH
 }
@@ -375,6 +419,7 @@ int b200_case_solidification_enable(b200_case* c, const double boxMin[3], const 
 {
     B200_TRY
     B200_CHECK(c && boxMin && boxMax, "solidification_enable: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
     c->p->solidificationEnable(boxMin, boxMax, isoValue, maxEvents);
     B200_CATCH
 }
@@ -382,6 +427,7 @@ int b200_case_solidification_events(b200_case* c, double* events, int64_t maxEve
 {
     B200_TRY
     B200_CHECK(c && nRecorded, "solidification_events: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
     *nRecorded = c->p->solidificationEvents(events, maxEvents);
     B200_CATCH
 }

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <string>
 #include <stdexcept>
+#include "solve_state.cuh"
 
 namespace b200 {
 
@@ -96,6 +97,10 @@ struct RedWork {
     double* partials;      // [nSlots][RED_MAX_BLOCKS]
     unsigned* ticket;      // one counter per reducing kernel in flight (serialised on one stream)
     double* result;        // [nSlots] final values
+    // single-rank solves: the Krylov control step that consumes this sum, run by the last block right after it wrote the
+    // result (C_NONE: the caller reduces over ranks first, or there is no control step)
+    int phase = C_NONE;
+    SolveState* state = nullptr;
 };
 
 // Called by every thread of every block after computing its private values v[0..N).
@@ -132,7 +137,10 @@ __device__ inline void grid_reduce(double (&v)[N], const int (&ops)[N], RedWork 
         double r = ops[i] == 0 ? block_reduce<Sum>(acc, smem) : ops[i] == 1 ? block_reduce<Max>(acc, smem) : block_reduce<Min>(acc, smem);
         if (tid == 0) w.result[slot0 + i] = r;
     }
-    if (tid == 0) *w.ticket = 0u;
+    if (tid == 0) {
+        *w.ticket = 0u;
+        if (w.phase != C_NONE) ctrl_apply(w.phase, w.state, w.result);
+    }
 }
 
 inline int red_blocks_for(int64_t n, int threads = RED_THREADS)

@@ -1,5 +1,6 @@
 #include "ctx.cuh"
 #include <cstring>
+#include <algorithm>
 
 namespace b200 {
 
@@ -59,6 +60,7 @@ Ctx::~Ctx()
     for (auto e : marks) if (e) cudaEventDestroy(e);
     for (int r = 0; r < nranks && peerOK; r++) if (r != rank && peers.p[r]) cudaIpcCloseMemHandle(peers.p[r]);
     if (myMail) cudaFree(myMail);
+    if (haloTicket) cudaFree(haloTicket);
     if (comm) ncclCommDestroy(comm);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -76,7 +78,10 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 // One warp: lane r pushes this rank's partials into rank r's mailbox (a peer store over NVLink, or a local store for
 // r == rank), then waits for rank r's partials in its own mailbox; lanes < n then sum the R partials in rank order.
-__global__ void k_peer_allreduce(PeerMail* mine, PeerPtrs peers, int rank, int nranks, unsigned long long seq, double* vals, int n, int op)
+// `phase` != C_NONE: lane 0 then runs the Krylov control step that consumes the sums (solve_state.cuh) -- `red` is the base of
+// the reduction slots, `vals` = red + slot0.
+__global__ void k_peer_allreduce(PeerMail* mine, PeerPtrs peers, int rank, int nranks, unsigned long long seq, double* vals, int n, int op,
+                                 const double* red, int phase, SolveState* st)
 {
     const int r = threadIdx.x;
     const int slot = (int)(seq % PEER_RING);
@@ -96,13 +101,19 @@ __global__ void k_peer_allreduce(PeerMail* mine, PeerPtrs peers, int rank, int n
         }
         vals[r] = acc;
     }
+    __syncwarp();
+    if (r == 0 && phase != C_NONE) ctrl_apply(phase, st, red);
 }
 
-void Ctx::peerExport(void* handle64)
+void Ctx::peerExport(void* handle64, size_t haloDoublesWanted)
 {
     if (!myMail) {
-        B200_CUDA(cudaMalloc(&myMail, sizeof(PeerMail)));
-        B200_CUDA(cudaMemset(myMail, 0, sizeof(PeerMail)));
+        haloDoubles = (haloDoublesWanted + 15) / 16 * 16;
+        const size_t bytes = sizeof(PeerMail) + 4 * haloDoubles * sizeof(double);
+        B200_CUDA(cudaMalloc(&myMail, bytes));
+        B200_CUDA(cudaMemset(myMail, 0, bytes));
+        B200_CUDA(cudaMalloc(&haloTicket, sizeof(unsigned)));
+        B200_CUDA(cudaMemset(haloTicket, 0, sizeof(unsigned)));
     }
     cudaIpcMemHandle_t h;
     B200_CUDA(cudaIpcGetMemHandle(&h, myMail));
@@ -130,21 +141,78 @@ void Ctx::allreduce(double* buf, int n, int op)
     if (nranks <= 1) return;
     if (peerOK) {
         B200_CHECK(n <= PEER_VALS, "peer all-reduce handles up to 8 values");
-        k_peer_allreduce<<<1, 32, 0, stream>>>(myMail, peers, rank, nranks, ++peerSeq, buf, n, op);
+        k_peer_allreduce<<<1, 32, 0, stream>>>(myMail, peers, rank, nranks, ++peerSeq, buf, n, op, nullptr, C_NONE, nullptr);
         B200_LAUNCH_CHECK();
         return;
     }
     const ncclRedOp_t o = op == 0 ? ncclSum : op == 1 ? ncclMax : ncclMin;
     B200_NCCL(ncclAllReduce(buf, buf, n, ncclDouble, o, comm, stream));
 }
+void Ctx::allreduceCtrl(double* red, int slot0, int n, int phase, SolveState* st)
+{
+    B200_CHECK(peerOK && n <= PEER_VALS, "allreduceCtrl needs the peer mailbox");
+    k_peer_allreduce<<<1, 32, 0, stream>>>(myMail, peers, rank, nranks, ++peerSeq, red + slot0, n, 0, red, phase, st);
+    B200_LAUNCH_CHECK();
+}
 void Ctx::allreduceSum(double* buf, int n) { allreduce(buf, n, 0); }
 void Ctx::allreduceMax(double* buf, int n) { allreduce(buf, n, 1); }
 void Ctx::allreduceMin(double* buf, int n) { allreduce(buf, n, 2); }
+
+// Plane exchange with the slab neighbours over peer memory, one kernel, no library call:
+//   1. every block stores its share of my bottom / top plane into the neighbour's window (peer stores over NVLink),
+//   2. the last block to finish (ticket) publishes the sequence number in the neighbour's haloFlag (release, system scope),
+//   3. every block waits for the neighbours' sequence number in MY flags and copies their planes from my window into my ghost
+//      planes (L1-bypassing loads: the lines were written by the peer).
+// No rank waits before it has pushed, so two ranks running this kernel cannot wait for each other in a cycle, whatever part of
+// the grid is resident.  Two window slots alternate: a neighbour's push number s+2 follows its wait for my push s+1, which follows
+// my pull of s in stream order.
+__global__ void __launch_bounds__(256) k_halo_exchange(const double* __restrict__ sendLo, double* __restrict__ recvLo, double* peerLoWin,
+                                                       unsigned long long* peerLoFlag, const double* __restrict__ sendHi,
+                                                       double* __restrict__ recvHi, double* peerHiWin, unsigned long long* peerHiFlag,
+                                                       const double* myWinFromLo, const unsigned long long* myFlagFromLo,
+                                                       const double* myWinFromHi, const unsigned long long* myFlagFromHi, size_t count,
+                                                       unsigned long long seq, unsigned* ticket)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x, i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (peerLoWin) for (size_t i = i0; i < count; i += stride) peerLoWin[i] = sendLo[i];
+    if (peerHiWin) for (size_t i = i0; i < count; i += stride) peerHiWin[i] = sendHi[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+            if (peerLoFlag) st_release_sys(peerLoFlag, seq);
+            if (peerHiFlag) st_release_sys(peerHiFlag, seq);
+            *ticket = 0u;
+        }
+        if (myFlagFromLo) while (ld_acquire_sys(myFlagFromLo) != seq) {}
+        if (myFlagFromHi) while (ld_acquire_sys(myFlagFromHi) != seq) {}
+    }
+    __syncthreads();
+    if (myWinFromLo) for (size_t i = i0; i < count; i += stride) recvLo[i] = __ldcg(myWinFromLo + i);
+    if (myWinFromHi) for (size_t i = i0; i < count; i += stride) recvHi[i] = __ldcg(myWinFromHi + i);
+}
 
 void Ctx::sendrecv(const double* sendLo, double* recvLo, int rankLo, const double* sendHi, double* recvHi, int rankHi,
                    size_t count)
 {
     if (nranks <= 1) return;
+    if (peerHaloOK(count)) {
+        const unsigned long long seq = ++haloSeq;
+        const int slot = (int)(seq & 1);
+        // my bottom plane goes to the rank below, where I am the neighbour ABOVE (side 1); my top plane to side 0 of the rank above
+        double* loWin = rankLo >= 0 ? haloWindow(peers.p[rankLo], 1, slot) : nullptr;
+        unsigned long long* loFlag = rankLo >= 0 ? &peers.p[rankLo]->haloFlag[1][slot] : nullptr;
+        double* hiWin = rankHi >= 0 ? haloWindow(peers.p[rankHi], 0, slot) : nullptr;
+        unsigned long long* hiFlag = rankHi >= 0 ? &peers.p[rankHi]->haloFlag[0][slot] : nullptr;
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 1023) / 1024, (size_t)smCount));
+        k_halo_exchange<<<grid, 256, 0, stream>>>(sendLo, recvLo, loWin, loFlag, sendHi, recvHi, hiWin, hiFlag,
+                                                  rankLo >= 0 ? haloWindow(myMail, 0, slot) : nullptr, rankLo >= 0 ? &myMail->haloFlag[0][slot] : nullptr,
+                                                  rankHi >= 0 ? haloWindow(myMail, 1, slot) : nullptr, rankHi >= 0 ? &myMail->haloFlag[1][slot] : nullptr,
+                                                  count, seq, haloTicket);
+        B200_LAUNCH_CHECK();
+        return;
+    }
     B200_NCCL(ncclGroupStart());
     if (rankLo >= 0) {
         B200_NCCL(ncclSend(sendLo, count, ncclDouble, rankLo, comm, stream));

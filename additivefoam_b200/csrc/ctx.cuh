@@ -26,7 +26,12 @@ constexpr int PEER_MAX_RANKS = 16, PEER_RING = 4, PEER_VALS = 8;
 struct PeerMail {
     double val[PEER_RING][PEER_MAX_RANKS][PEER_VALS];
     unsigned long long flag[PEER_RING][PEER_MAX_RANKS];
+    // halo window (follows this struct in the same allocation): haloFlag[side][slot] = sequence number of the plane that the
+    // neighbour on that side (0 = rank below, 1 = rank above) has finished storing into slot `slot` of my window
+    unsigned long long haloFlag[2][2];
+    unsigned long long pad_[12];          // the window starts on a 128-byte boundary
 };
+static_assert(sizeof(PeerMail) % 128 == 0, "halo window alignment");
 struct PeerPtrs { PeerMail* p[PEER_MAX_RANKS]; };
 
 struct Ctx {
@@ -35,9 +40,20 @@ struct Ctx {
     PeerPtrs peers{};
     bool peerOK = false;
     unsigned long long peerSeq = 0;
-    void peerExport(void* handle64);
+    // Halo planes over NVLink without NCCL: behind the mailbox, in the same IPC allocation, every rank keeps a window of
+    // [2 sides][2 slots][haloDoubles]; a neighbour stores its boundary plane straight into it (k_halo_exchange, ctx.cu).
+    size_t haloDoubles = 0;
+    unsigned long long haloSeq = 0;
+    unsigned* haloTicket = nullptr;
+    double* haloWindow(PeerMail* base, int side, int slot) const
+    {
+        return reinterpret_cast<double*>(reinterpret_cast<char*>(base) + sizeof(PeerMail)) + ((size_t)side * 2 + slot) * haloDoubles;
+    }
+    bool peerHaloOK(size_t count) const { return peerOK && haloDoubles >= count && count > 0; }
+    void peerExport(void* handle64, size_t haloDoublesWanted = 0);
     void peerImport(const void* handles);     // nranks x 64 bytes, rank order
     void allreduce(double* buf, int n, int op);   // op: 0 sum, 1 max, 2 min
+    void allreduceCtrl(double* red, int slot0, int n, int phase, SolveState* st);   // sum + the control step that consumes it, one kernel
     // profiler: one event pair per instrumented launch group, resolved at read time
     bool profOn = false;
     struct ProfRec { int cat; cudaEvent_t a, b; };

@@ -235,15 +235,34 @@ void Ldu::exchange(const double* x)
     B200_NCCL(ncclGroupEnd());
 }
 
-void Ldu::allreduce(int slot0, int n)
+// After a kernel left a local sum in red.result[slot0 .. slot0+n): make it global and run the Krylov control step `phase` that
+// consumes it.  One rank: the producing kernel's last block already ran the step (redFor(phase)) -- nothing to launch.  Several
+// ranks: the peer all-reduce kernel runs it (one launch for both); over NCCL a k_ctrl launch follows the library call.
+void Ldu::reduceCtrl(int slot0, int n, int phase)
 {
     if (ctx->nranks <= 1) return;
-    ProfScope ps_(ctx, PC_COMM);
-    ctx->allreduceSum(red.result + slot0, n);
+    if (ctx->peerOK) {
+        ProfScope ps_(ctx, PC_COMM);
+        ctx->allreduceCtrl(red.result, slot0, n, phase, d_state);
+        return;
+    }
+    { ProfScope ps_(ctx, PC_COMM); ctx->allreduceSum(red.result + slot0, n); }
+    if (phase != C_NONE) {
+        ProfScope ps_(ctx, PC_CTRL);
+        k_ctrl<<<1, 1, 0, ctx->stream>>>(phase, d_state, red.result);
+        B200_LAUNCH_CHECK();
+    }
+}
+
+RedWork Ldu::redFor(int phase) const
+{
+    RedWork r = red;
+    if (ctx->nranks <= 1) { r.phase = phase; r.state = d_state; }
+    return r;
 }
 
 // ------------------------------------------------------------------ Amul
-template <int MODE> static void launch_amul(Ldu& L, const MatrixView& A, const double* x, double* y, const double* aux, const SolveState* st)
+template <int MODE> static void launch_amul(Ldu& L, const MatrixView& A, const double* x, double* y, const double* aux, const SolveState* st, const RedWork& red)
 {
     cudaStream_t s = L.ctx->stream;
     ProfScope ps_(L.ctx, PC_AMUL);
@@ -252,26 +271,29 @@ template <int MODE> static void launch_amul(Ldu& L, const MatrixView& A, const d
         const double* ba = (L.ghostAbove && A.bouCoeffs) ? A.bouCoeffs[L.ghostBelow ? 1 : 0] : nullptr;
         const int64_t items = (int64_t)((L.dims.nx + BLK - 1) / BLK) * L.dims.ny * L.dims.nz;
         const int grid = (int)std::min<int64_t>(items, L.ctx->persistentBlocks());
-        k_amul_block<MODE><<<grid, BLK, 0, s>>>(L.dims, A.diag, A.upper, A.lower, x, y, aux, bb, ba, L.red, st);
+        k_amul_block<MODE><<<grid, BLK, 0, s>>>(L.dims, A.diag, A.upper, A.lower, x, y, aux, bb, ba, red, st);
     } else {
         k_amul_general<MODE><<<L.redBlocks, BLK, 0, s>>>(L.nCells, L.d_rowStart, L.d_rowMid, L.d_rowCol, L.d_rowFace, A.diag, A.upper,
-                                                         A.lower, x, y, aux, L.red, st);
+                                                         A.lower, x, y, aux, red, st);
     }
     B200_LAUNCH_CHECK();
 }
 
-void Ldu::amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux)
+// y = A x with the sum `mode` fused in; `phase` = the control step that consumes that sum (the caller follows up with
+// reduceCtrl(slot, n, phase), which is a no-op on one rank)
+void Ldu::amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux, int phase)
 {
     const SolveState* st = d_state;
     exchange(x);
     const bool post = !ifaces.empty();       // general coupled interfaces: apply after the gather, reduce separately
     const int m = post ? AM_NONE : mode;
+    const RedWork rw = redFor(phase);
     switch (m) {
-    case AM_NONE: launch_amul<AM_NONE>(*this, A, x, y, aux, st); break;
-    case AM_SUMX: launch_amul<AM_SUMX>(*this, A, x, y, aux, st); break;
-    case AM_DOT_YX: launch_amul<AM_DOT_YX>(*this, A, x, y, aux, st); break;
-    case AM_DOT_AUXY: launch_amul<AM_DOT_AUXY>(*this, A, x, y, aux, st); break;
-    case AM_TT_TS: launch_amul<AM_TT_TS>(*this, A, x, y, aux, st); break;
+    case AM_NONE: launch_amul<AM_NONE>(*this, A, x, y, aux, st, rw); break;
+    case AM_SUMX: launch_amul<AM_SUMX>(*this, A, x, y, aux, st, rw); break;
+    case AM_DOT_YX: launch_amul<AM_DOT_YX>(*this, A, x, y, aux, st, rw); break;
+    case AM_DOT_AUXY: launch_amul<AM_DOT_AUXY>(*this, A, x, y, aux, st, rw); break;
+    case AM_TT_TS: launch_amul<AM_TT_TS>(*this, A, x, y, aux, st, rw); break;
     }
     if (!post) return;
     cudaStream_t s = ctx->stream;
@@ -281,7 +303,7 @@ void Ldu::amulFused(const MatrixView& A, const double* x, double* y, int mode, c
         k_iface_apply<<<grid, BLK, 0, s>>>(it.size, it.faceCells, A.bouCoeffs[p], it.recvBuf, y, it.hasDuplicates ? 1 : 0, st);
         B200_LAUNCH_CHECK();
     }
-    const int64_t n = nCells;
+    const int64_t n = nCells;      // (coupled interfaces mean several ranks: the control step runs in reduceCtrl)
     if (mode == AM_SUMX) { k_sum<<<redBlocks, BLK, 0, s>>>(n, x, red, S_SUMPSI); B200_LAUNCH_CHECK(); }
     else if (mode == AM_DOT_YX) { k_dot<<<redBlocks, BLK, 0, s>>>(n, y, x, red, S_DEN, st); B200_LAUNCH_CHECK(); }
     else if (mode == AM_DOT_AUXY) { k_dot<<<redBlocks, BLK, 0, s>>>(n, aux, y, red, S_DEN, st); B200_LAUNCH_CHECK(); }
@@ -295,7 +317,7 @@ void Ldu::amul(const MatrixView& A, const double* psi, double* Apsi)
 {
     ensureWork();
     B200_CUDA(cudaMemsetAsync(d_state, 0, sizeof(SolveState), ctx->stream));
-    amulFused(A, psi, Apsi, AM_NONE, nullptr);
+    amulFused(A, psi, Apsi, AM_NONE, nullptr, C_NONE);
 }
 
 // ------------------------------------------------------------------ tile-wavefront sweeps (block addressing)
@@ -357,7 +379,7 @@ int Ldu::waveVecGrid()
 }
 
 // op: 0 factor (after the gather), 1 forward, 2 backward
-void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio)
+void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio, int phase)
 {
     WaveArgs a;
     a.g = wave_geom(dims);
@@ -450,7 +472,7 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
             std::fprintf(stderr, "\n");
         }
     }
-    if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result + S_RHO, d_state); B200_LAUNCH_CHECK(); }
+    if (op == 2 && dot) { k_wave_sum<<<1, 256, 0, s>>>(a.g.nTiles, wavePartial, red.result, (int)S_RHO, d_state, ctx->nranks <= 1 ? phase : (int)C_NONE); B200_LAUNCH_CHECK(); }
 }
 
 // ------------------------------------------------------------------ preconditioners
@@ -488,7 +510,7 @@ void Ldu::factor(int kind, const MatrixView& A)
                 B200_LAUNCH_CHECK();
                 waveEpoch = A.offDiagEpoch; waveUpper = A.upper; waveLower = A.lower; waveDilu = dilu;
             }
-            waveSweep(0, dilu, false, A.diag, nullptr, false);
+            waveSweep(0, dilu, false, A.diag, nullptr, false, C_NONE);
             return;          // rD lives in wave order (A0)
         } else if (isBlock) {
             if (dilu) coop_launch(ctx, k_sweep_block<0, true, false>, (int64_t)dims.ny * dims.nz, dims, A.diag, A.upper, A.lower, rd, nul, nulw, nul, red, 0, st);
@@ -511,7 +533,7 @@ void Ldu::factor(int kind, const MatrixView& A)
             k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowRD, st); B200_LAUNCH_CHECK();
             k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowF, st); B200_LAUNCH_CHECK();
             k_fill_sentinel<<<grid, BLK, 0, s>>>((int64_t)nCells, flowB, st); B200_LAUNCH_CHECK();
-            flowSweep(0, dilu, false, A, nullptr, nullptr, nullptr);
+            flowSweep(0, dilu, false, A, nullptr, nullptr, nullptr, C_NONE);
             k_reciprocal<<<redBlocks, BLK, 0, s>>>((int64_t)nCells, flowRD, st); B200_LAUNCH_CHECK();
             return;              // rD lives in position order (flowRD)
         } else {
@@ -524,7 +546,7 @@ void Ldu::factor(int kind, const MatrixView& A)
 }
 
 // what: 0 factor recurrence (rD sentinel-filled by the caller), 1 forward, 2 backward (+ dot into S_RHO)
-void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec)
+void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec, int phase)
 {
     cudaStream_t s = ctx->stream;
     const int nChunks = (nCells + 31) / 32;              // one per warp ticket
@@ -552,39 +574,40 @@ void Ldu::flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const do
     else if (dot) k_sweep_flow<2, true><<<grid, BLK, 0, s>>>(a);
     else k_sweep_flow<2, false><<<grid, BLK, 0, s>>>(a);
     B200_LAUNCH_CHECK();
-    if (what == 2 && dot) { k_sum<<<red_blocks_for(nChunks), BLK, 0, s>>>((int64_t)nChunks, flowPartial, red, (int)S_RHO, d_state); B200_LAUNCH_CHECK(); }
+    if (what == 2 && dot) { k_sum<<<red_blocks_for(nChunks), BLK, 0, s>>>((int64_t)nChunks, flowPartial, redFor(phase), (int)S_RHO, d_state); B200_LAUNCH_CHECK(); }
 }
 
 // wA = M^-1 rA, optionally with sum(wA . dotVec) into slot S_RHO
-void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int doDot, const double* dotVec, bool wio)
+void Ldu::applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int doDot, const double* dotVec, bool wio, int phase)
 {
     cudaStream_t s = ctx->stream;
     const SolveState* st = d_state;
     double* rd = rD + ghost;
-    if (kind == 0) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<false><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
-    if (kind == 1) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<true><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, red, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
+    const RedWork rw = redFor(doDot ? phase : (int)C_NONE);
+    if (kind == 0) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<false><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, rw, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
+    if (kind == 1) { ProfScope ps_(ctx, PC_VECTOR); k_precond_pointwise<true><<<redBlocks, BLK, 0, s>>>((int64_t)nCells, rd, rA, wA, dotVec, rw, S_RHO, doDot, st); B200_LAUNCH_CHECK(); return; }
     const bool dilu = kind == 3;
     const double* nul = nullptr;
     if (isBlock && useWave) {
-        { ProfScope ps_(ctx, PC_SWEEP_FWD); waveSweep(1, dilu, false, rA, wA, wio); }
-        { ProfScope ps_(ctx, PC_SWEEP_BWD); waveSweep(2, dilu, doDot != 0, rA, wA, wio); }
+        { ProfScope ps_(ctx, PC_SWEEP_FWD); waveSweep(1, dilu, false, rA, wA, wio, C_NONE); }
+        { ProfScope ps_(ctx, PC_SWEEP_BWD); waveSweep(2, dilu, doDot != 0, rA, wA, wio, phase); }
         B200_CHECK(!doDot || dotVec == rA, "fused preconditioner dot product is defined against rA");
     } else if (isBlock) {
         const int64_t work_ = (int64_t)dims.ny * dims.nz;
         if (dilu) { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, true, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
         else { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_block<1, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
-        if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, true>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st); }
+        if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, true>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, rw, (int)S_RHO, st); }
         else { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_block<2, false, false>, work_, dims, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
     } else if (useFlow) {
-        { ProfScope ps_(ctx, PC_SWEEP_FWD); flowSweep(1, dilu, false, A, rA, wA, nullptr); }
-        { ProfScope ps_(ctx, PC_SWEEP_BWD); flowSweep(2, dilu, doDot != 0, A, rA, wA, dotVec); }
+        { ProfScope ps_(ctx, PC_SWEEP_FWD); flowSweep(1, dilu, false, A, rA, wA, nullptr, C_NONE); }
+        { ProfScope ps_(ctx, PC_SWEEP_BWD); flowSweep(2, dilu, doDot != 0, A, rA, wA, dotVec, phase); }
     } else {
         const int* ls = d_lvlStart; const int* lc = d_lvlCells; const int* rs = d_rowStart; const int* rm = d_rowMid;
         const int* rc = d_rowCol; const int* rf = d_rowFace;
         const int64_t work_ = maxLevelSize;
         if (dilu) { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_general<1, true, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
         else { ProfScope ps_(ctx, PC_SWEEP_FWD); coop_launch(ctx, k_sweep_general<1, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
-        if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_general<2, false, true>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, red, (int)S_RHO, st); }
+        if (doDot) { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_general<2, false, true>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, dotVec, rw, (int)S_RHO, st); }
         else { ProfScope ps_(ctx, PC_SWEEP_BWD); coop_launch(ctx, k_sweep_general<2, false, false>, work_, nLevels, ls, lc, rs, rm, rc, rf, A.diag, A.upper, A.lower, rd, rA, wA, nul, red, 0, st); }
     }
 }
@@ -594,14 +617,14 @@ void Ldu::precondition(int kind, const MatrixView& A, const double* rA, double* 
     ensureWork();
     B200_CUDA(cudaMemsetAsync(d_state, 0, sizeof(SolveState), ctx->stream));
     factor(kind, A);
-    applyPrecond(kind, A, rA, wA, 0, nullptr, false);
+    applyPrecond(kind, A, rA, wA, 0, nullptr, false, C_NONE);
 }
 
 // ------------------------------------------------------------------ Krylov drivers
 static void ctrl(Ldu& L, int phase)
 {
     ProfScope ps_(L.ctx, PC_CTRL);
-    k_ctrl<<<1, 1, 0, L.ctx->stream>>>(phase, L.d_state, L.red.result, &L.d_state->early);
+    k_ctrl<<<1, 1, 0, L.ctx->stream>>>(phase, L.d_state, L.red.result);
     B200_LAUNCH_CHECK();
 }
 
@@ -638,10 +661,10 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     double *wA = vec(0), *pA = vec(1), *rA = vec(2), *qA = vec(3);
     double *yA = vec(0), *AyA = vec(3), *sA = vec(4), *zA = vec(5), *tA = vec(6), *rA0 = vec(7);
 
-    // wA = A psi (+ sum psi); rA = source - wA; normFactor
-    amulFused(A, psi, wA, AM_SUMX, nullptr);
-    allreduce(S_SUMPSI, 1);
-    ctrl(*this, C_AVG);
+    // wA = A psi (+ sum psi); rA = source - wA; normFactor.  Every global sum is followed by the control step that consumes it,
+    // fused into the kernel that completes the sum (reduceCtrl / redFor).
+    amulFused(A, psi, wA, AM_SUMX, nullptr, C_AVG);
+    reduceCtrl(S_SUMPSI, 1, C_AVG);
     if (isBlock) {
         const double* bb = (ghostBelow && A.bouCoeffs) ? A.bouCoeffs[0] : nullptr;
         const double* ba = (ghostAbove && A.bouCoeffs) ? A.bouCoeffs[ghostBelow ? 1 : 0] : nullptr;
@@ -649,7 +672,7 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
         const int grid = (int)std::min<int64_t>(items, ctx->persistentBlocks());
         B200_CHECK(ifaces.empty(), "block addressing with general interfaces: use ghost planes");
         ProfScope ps_(ctx, PC_NORMFACTOR);
-        k_normfactor_block<<<grid, BLK, 0, s>>>(dims, A.diag, A.upper, A.lower, bb, ba, source, wA, rA, red, st);
+        k_normfactor_block<<<grid, BLK, 0, s>>>(dims, A.diag, A.upper, A.lower, bb, ba, source, wA, rA, redFor(C_INIT), st);
         B200_LAUNCH_CHECK();
     } else {
         ProfScope ps_(ctx, PC_NORMFACTOR);
@@ -662,11 +685,10 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
             k_iface_sumA<<<grid, BLK, 0, s>>>(it.size, it.faceCells, A.bouCoeffs[p], d_sumA, it.hasDuplicates ? 1 : 0);
             B200_LAUNCH_CHECK();
         }
-        k_normfactor_general<<<redBlocks, BLK, 0, s>>>(nCells, d_sumA, source, wA, rA, red, st);
+        k_normfactor_general<<<redBlocks, BLK, 0, s>>>(nCells, d_sumA, source, wA, rA, redFor(C_INIT), st);
         B200_LAUNCH_CHECK();
     }
-    allreduce(S_NORM, 2);
-    ctrl(*this, C_INIT);
+    reduceCtrl(S_NORM, 2, C_INIT);
     factor(sc.precond, A);
     // PCG with a DIC/DILU wave sweep keeps the residual (RF) and the preconditioned residual (WB) in wave order: the sweeps
     // then stream whole rows only, and the two vector updates transpose through shared memory (wave_kernels.cuh)
@@ -683,59 +705,56 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     if (!pcg) { { ProfScope ps_(ctx, PC_VECTOR); k_copy<<<redBlocks, BLK, 0, s>>>(n, rA, rA0, st); B200_LAUNCH_CHECK(); } }
 
     const int hardMax = std::max(sc.maxIter + 1, sc.minIter);
-    // Large systems: look at the convergence flag after every iteration (one tiny D2H + sync against milliseconds of
-    // kernels), so no launch is wasted; small systems: enqueue several iterations per look, later ones become no-ops.
-    const bool perIteration = nCells >= (1 << 20);
-    int enqueued = 0, chunk = perIteration ? 1 : 2;
+    // The host only looks at the device's `done` flag (one tiny D2H + sync); iterations enqueued past convergence are no-ops.
+    // How many iterations go out before the first look, and per look afterwards, must be the same on every rank -- each
+    // iteration enqueues halo exchanges and all-reduces that pair up across ranks -- so the policy uses rank-invariant
+    // numbers only: the iteration count of the previous solve on this addressing (a global result; the resident stepper's
+    // solves with the shipped controls all run to maxIter + 1) and the global cell count per rank.
+    const bool large = nGlobalCells / ctx->nranks >= (double)(1 << 20);
+    int enqueued = 0;
+    int chunk = lastIterations > 0 ? std::min(lastIterations, hardMax) : (large ? 1 : 2);
     for (;;) {
         for (int it = 0; it < chunk && enqueued < hardMax; it++, enqueued++) {
             if (pcg) {
-                applyPrecond(sc.precond, A, rA, wA, 1, rA, wio);    // wA = M^-1 rA ; wArA
-                allreduce(S_RHO, 1);
-                ctrl(*this, C_PCG_BETA);
+                applyPrecond(sc.precond, A, rA, wA, 1, rA, wio, C_PCG_BETA);    // wA = M^-1 rA ; wArA
+                reduceCtrl(S_RHO, 1, C_PCG_BETA);
                 { ProfScope ps_(ctx, PC_VECTOR);
                   if (wio) k_wave_pcg_p<<<wioGrid, 256, 0, s>>>(wg, wave[9], pA, st);
                   else k_pcg_p<<<redBlocks, BLK, 0, s>>>(n, wA, pA, st);
                   B200_LAUNCH_CHECK(); }
-                amulFused(A, pA, qA, AM_DOT_YX, nullptr);           // q = A pA ; wApA
-                allreduce(S_DEN, 1);
-                ctrl(*this, C_PCG_ALPHA);
+                amulFused(A, pA, qA, AM_DOT_YX, nullptr, C_PCG_ALPHA);          // q = A pA ; wApA
+                reduceCtrl(S_DEN, 1, C_PCG_ALPHA);
                 { ProfScope ps_(ctx, PC_VECTOR);
-                  if (wio) k_wave_pcg_update<<<wioGrid, 256, 0, s>>>(wg, pA, qA, psi, wave[8], red, st);
-                  else k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, red, st);
+                  if (wio) k_wave_pcg_update<<<wioGrid, 256, 0, s>>>(wg, pA, qA, psi, wave[8], redFor(C_ITER_END), st);
+                  else k_pcg_update<<<redBlocks, BLK, 0, s>>>(n, pA, qA, psi, rA, redFor(C_ITER_END), st);
                   B200_LAUNCH_CHECK(); }
-                allreduce(S_MAGR, 1);
-                ctrl(*this, C_ITER_END);
+                reduceCtrl(S_MAGR, 1, C_ITER_END);
             } else {
-                { ProfScope ps_(ctx, PC_VECTOR); k_dot<<<redBlocks, BLK, 0, s>>>(n, rA0, rA, red, S_RHO, st); B200_LAUNCH_CHECK(); }
-                allreduce(S_RHO, 1);
-                ctrl(*this, C_BICG_RHO);
+                { ProfScope ps_(ctx, PC_VECTOR); k_dot<<<redBlocks, BLK, 0, s>>>(n, rA0, rA, redFor(C_BICG_RHO), S_RHO, st); B200_LAUNCH_CHECK(); }
+                reduceCtrl(S_RHO, 1, C_BICG_RHO);
                 { ProfScope ps_(ctx, PC_VECTOR); k_bicg_p<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, pA, st); B200_LAUNCH_CHECK(); }
-                applyPrecond(sc.precond, A, pA, yA, 0, nullptr, false);
-                amulFused(A, yA, AyA, AM_DOT_AUXY, rA0);            // rA0 . AyA
-                allreduce(S_DEN, 1);
-                ctrl(*this, C_BICG_ALPHA);
-                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_s<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, sA, red, st); B200_LAUNCH_CHECK(); }
-                allreduce(S_MAGR, 1);
-                ctrl(*this, C_BICG_SCHECK);
+                applyPrecond(sc.precond, A, pA, yA, 0, nullptr, false, C_NONE);
+                amulFused(A, yA, AyA, AM_DOT_AUXY, rA0, C_BICG_ALPHA);          // rA0 . AyA
+                reduceCtrl(S_DEN, 1, C_BICG_ALPHA);
+                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_s<<<redBlocks, BLK, 0, s>>>(n, rA, AyA, sA, redFor(C_BICG_SCHECK), st); B200_LAUNCH_CHECK(); }
+                reduceCtrl(S_MAGR, 1, C_BICG_SCHECK);
                 { ProfScope ps_(ctx, PC_VECTOR); k_bicg_early<<<redBlocks, BLK, 0, s>>>(n, yA, psi, st, &d_state->early); B200_LAUNCH_CHECK(); }
                 ctrl(*this, C_BICG_EARLY_END);
-                applyPrecond(sc.precond, A, sA, zA, 0, nullptr, false);
-                amulFused(A, zA, tA, AM_TT_TS, sA);                 // tA.tA, tA.sA
-                allreduce(S_TT, 2);
-                ctrl(*this, C_BICG_OMEGA);
-                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_update<<<redBlocks, BLK, 0, s>>>(n, yA, zA, sA, tA, psi, rA, red, st); B200_LAUNCH_CHECK(); }
-                allreduce(S_MAGR2, 1);
-                ctrl(*this, C_ITER_END2);
+                applyPrecond(sc.precond, A, sA, zA, 0, nullptr, false, C_NONE);
+                amulFused(A, zA, tA, AM_TT_TS, sA, C_BICG_OMEGA);               // tA.tA, tA.sA
+                reduceCtrl(S_TT, 2, C_BICG_OMEGA);
+                { ProfScope ps_(ctx, PC_VECTOR); k_bicg_update<<<redBlocks, BLK, 0, s>>>(n, yA, zA, sA, tA, psi, rA, redFor(C_ITER_END2), st); B200_LAUNCH_CHECK(); }
+                reduceCtrl(S_MAGR2, 1, C_ITER_END2);
             }
         }
         d2h(h_state, d_state, 1, s);
         ctx->sync();
         if (h_state->done || enqueued >= hardMax) break;
-        if (!perIteration) chunk = std::min(chunk * 2, 32);
+        chunk = large ? 1 : std::min(std::max(chunk, 1) * 2, 32);
     }
     perf.initialResidual = h_state->initRes; perf.finalResidual = h_state->finalRes;
     perf.nIterations = h_state->nIter; perf.converged = h_state->converged; perf.singular = h_state->singular;
+    lastIterations = perf.nIterations;
     return perf;
 }
 

@@ -67,15 +67,6 @@ struct SolvePerf {
     int nIterations = 0, converged = 0, singular = 0;
 };
 
-// scalar state of a running solve, resident on the device
-struct SolveState {
-    double tol, relTol, nGlobal;
-    int minIter, maxIter;
-    double avgPsi, normFactor, initRes, finalRes;
-    double wArA, wArAold, wApA, alpha, beta, omega, rA0rA, rA0rAold, rA0AyA;
-    int nIter, done, converged, singular, early;
-};
-
 class Ldu {
 public:
     Ldu(Ctx* ctx, int nCells, int nFaces, const int* lower, const int* upper, int nInterfaces,
@@ -133,18 +124,20 @@ public:
     double *flowRD = nullptr, *flowF = nullptr, *flowB = nullptr;             // position-ordered rD, forward and backward results
     double* flowPartial = nullptr;   // per-chunk sums of the fused dot product
     int* flowTicket = nullptr;
-    void flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec);
+    void flowSweep(int what, bool dilu, bool dot, const MatrixView& A, const double* rA, double* wA, const double* dotVec, int phase);
     void ensureWave(bool dilu);
-    void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio);
+    void waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, bool wio, int phase);
     int waveVecGrid();
 
     void ensureWork();
     double* vec(int i) { return work[i] + ghost; }
     void factor(int kind, const MatrixView& A);
-    void applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int dotMode, const double* dotVec, bool wio);
-    void amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux);
+    void applyPrecond(int kind, const MatrixView& A, const double* rA, double* wA, int dotMode, const double* dotVec, bool wio, int phase);
+    void amulFused(const MatrixView& A, const double* x, double* y, int mode, const double* aux, int phase);
     void exchange(const double* x);   // interface / ghost-plane update before an Amul on x
-    void allreduce(int slot0, int n);
+    void reduceCtrl(int slot0, int n, int phase);
+    RedWork redFor(int phase) const;
+    int lastIterations = 0;          // iteration count of the previous solve (look-ahead of the host loop, rank-invariant)
 };
 
 // wave_kernels.cuh's shared-reciprocal division against the compiler's operator on n pseudo-random pairs; returns the mismatches

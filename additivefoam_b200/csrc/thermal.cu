@@ -158,6 +158,11 @@ ThermalCase::~ThermalCase()
     dev_free(red.partials); dev_free(red.ticket); dev_free(red.result);
     if (h_red) cudaFreeHost(h_red);
     dev_free(solidEv); dev_free(solidKeys); dev_free(solidCount);
+    if (h2dStream) { cudaStreamSynchronize(h2dStream); cudaStreamSynchronize(d2hStream); cudaStreamDestroy(h2dStream); cudaStreamDestroy(d2hStream); }
+    for (int f = 0; f < NIOF; f++) {
+        dev_free(stageIn[f]); dev_free(stageOut[f]);
+        for (cudaEvent_t e : {evIn[f], evInFree[f], evOutReady[f], evOutDone[f]}) if (e) cudaEventDestroy(e);
+    }
     for (auto& si : sides) { dev_free(si.valueFraction); dev_free(si.Tb); dev_free(si.intCoeff); dev_free(si.bouCoeff); }
 }
 
@@ -172,6 +177,8 @@ double* ThermalCase::field(int f)
     case B200_FIELD_QDOT: return qDot;
     case B200_FIELD_DFDT: return dFdT;
     case B200_FIELD_T0: return T0;
+    case B200_FIELD_T_OLD: return Told;
+    case B200_FIELD_ALPHA_SOLID_OLD: return alpha1old;
     }
     throw Error("unknown field id");
 }
@@ -194,6 +201,69 @@ void ThermalCase::setField(int fIn, const double* in)
         evaluateT();
     }
     if (f == B200_FIELD_ALPHA_SOLID) B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    ctx->sync();
+}
+
+// ---- streamed host I/O.  The host side of a step is then: inputs of the NEXT step cross PCIe on `h2dStream` while this step's
+// kernels run, results of THIS step cross on `d2hStream` while the next step's kernels run; the compute stream only pays two
+// device-to-device copies per field.  Host buffers must be pinned (cudaMemcpyAsync from pageable memory would serialise).
+void ThermalCase::ensureIo(int f, bool out)
+{
+    B200_CHECK(f >= 0 && f < NIOF, "field id out of range");
+    if (!h2dStream) {
+        B200_CUDA(cudaStreamCreateWithFlags(&h2dStream, cudaStreamNonBlocking));
+        B200_CUDA(cudaStreamCreateWithFlags(&d2hStream, cudaStreamNonBlocking));
+    }
+    double*& buf = out ? stageOut[f] : stageIn[f];
+    if (!buf) {
+        buf = dev_alloc<double>((size_t)dims.nCells());
+        if (out) { B200_CUDA(cudaEventCreateWithFlags(&evOutReady[f], cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&evOutDone[f], cudaEventDisableTiming)); }
+        else { B200_CUDA(cudaEventCreateWithFlags(&evIn[f], cudaEventDisableTiming)); B200_CUDA(cudaEventCreateWithFlags(&evInFree[f], cudaEventDisableTiming)); }
+    }
+}
+
+// host -> staging buffer on the H2D stream; returns at once.  The field itself changes at the next applyStaged().
+void ThermalCase::setFieldAsync(int f, const double* in)
+{
+    (void)field(f);
+    ensureIo(f, false);
+    B200_CUDA(cudaStreamWaitEvent(h2dStream, evInFree[f], 0));          // the previous staged value has been consumed (no-op the first time)
+    B200_CUDA(cudaMemcpyAsync(stageIn[f], in, (size_t)dims.nCells() * sizeof(double), cudaMemcpyHostToDevice, h2dStream));
+    B200_CUDA(cudaEventRecord(evIn[f], h2dStream));
+    inPending[f] = true;
+}
+
+// staged inputs become the fields, on the compute stream (upload-only semantics of B200_FIELD_KEEP_OLD: the host owns the
+// fields between steps, old-time copies follow at the step's own runTime++)
+void ThermalCase::applyStaged()
+{
+    for (int f = 0; f < NIOF; f++) {
+        if (!inPending[f]) continue;
+        B200_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[f], 0));
+        B200_CUDA(cudaMemcpyAsync(field(f), stageIn[f], (size_t)dims.nCells() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        B200_CUDA(cudaEventRecord(evInFree[f], ctx->stream));
+        inPending[f] = false;
+    }
+}
+
+// snapshot of the field on the compute stream, then staging buffer -> host on the D2H stream; returns at once
+void ThermalCase::getFieldAsync(int f, double* out)
+{
+    double* src = field(f);
+    ensureIo(f, true);
+    B200_CUDA(cudaStreamWaitEvent(ctx->stream, evOutDone[f], 0));       // the previous snapshot has left the device
+    B200_CUDA(cudaMemcpyAsync(stageOut[f], src, (size_t)dims.nCells() * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    B200_CUDA(cudaEventRecord(evOutReady[f], ctx->stream));
+    B200_CUDA(cudaStreamWaitEvent(d2hStream, evOutReady[f], 0));
+    B200_CUDA(cudaMemcpyAsync(out, stageOut[f], (size_t)dims.nCells() * sizeof(double), cudaMemcpyDeviceToHost, d2hStream));
+    B200_CUDA(cudaEventRecord(evOutDone[f], d2hStream));
+}
+
+void ThermalCase::transfersWait()
+{
+    if (!h2dStream) return;
+    B200_CUDA(cudaStreamSynchronize(h2dStream));
+    B200_CUDA(cudaStreamSynchronize(d2hStream));
     ctx->sync();
 }
 

@@ -66,6 +66,11 @@ public:
     int64_t nGlobal() const { return (int64_t)dims.nx * dims.ny * nzGlobal; }
     void getField(int field, double* out);
     void setField(int field, const double* in);
+    // streamed host I/O (b200_case_set_field_async / apply_staged / get_field_async / transfers_wait)
+    void setFieldAsync(int field, const double* pinnedIn);
+    void applyStaged();
+    void getFieldAsync(int field, double* pinnedOut);
+    void transfersWait();
     void isothermDepthProbe(int beam, const double position[3], double dimensionsOut[3]);
     void sourcesUpdate(double proposedDeltaT, double* deltaTOut);
     void meltPoolDimensions(int nIso, const double* isoValues, double scanPathAngleDeg, double* dims);
@@ -112,6 +117,14 @@ private:
     unsigned long long* solidCount = nullptr;
     int64_t solidMax = 0, solidExec = 0;
     void solidificationExecute();
+
+    // streamed host I/O: two copy streams beside the compute stream, one staging buffer per field and direction
+    static constexpr int NIOF = 10;
+    cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
+    double* stageIn[NIOF] = {nullptr}; double* stageOut[NIOF] = {nullptr};
+    cudaEvent_t evIn[NIOF] = {nullptr}, evInFree[NIOF] = {nullptr}, evOutReady[NIOF] = {nullptr}, evOutDone[NIOF] = {nullptr};
+    bool inPending[NIOF] = {false};
+    void ensureIo(int f, bool out);
 
     double* field(int f);
     double* allocField();

@@ -340,6 +340,12 @@ def _read_controls(case_dir):
     if precond not in _PRECONDS:
         raise FoamCaseError(f"preconditioner {precond}")
     pimple = f.get("PIMPLE", {})
+    # pU (SOLVER/pU/*, additiveFoam.C:78-88) is not built: a case that asks for the momentum/pressure loop would silently run as
+    # pure conduction, so it is refused (tutorials/verificationAndValidation/marangoni has nOuterCorrectors 1)
+    if int(pimple.get("nOuterCorrectors", 0)) > 0:
+        raise FoamCaseError("PIMPLE nOuterCorrectors > 0 asks for the pU loop and fvm::div(phi,T) with phi != 0, which the library "
+                            "does not implement (thermal path only)")
+    _check_schemes(case_dir)
     adjustable = c.get("writeControl") == "adjustableRunTime"
     return dict(startTime=float(c.get("startTime", 0.0)), endTime=float(c["endTime"]), deltaT=float(c["deltaT"]),
                 adjustTimeStep=_switch(c["adjustTimeStep"], "adjustTimeStep") if "adjustTimeStep" in c else 0,
@@ -350,6 +356,39 @@ def _read_controls(case_dir):
                 explicitSolve=_switch(pimple["explicitSolve"], "explicitSolve") if "explicitSolve" in pimple else 0,
                 solver=_SOLVERS[ts["solver"]], preconditioner=_PRECONDS[precond], tolerance=float(ts.get("tolerance", 1e-6)),
                 relTol=float(ts.get("relTol", 0.0)), minIter=int(ts.get("minIter", 0)), maxIter=int(ts.get("maxIter", 1000)))
+
+
+def _scheme(d, section, *keys):
+    """The entry of fvSchemes `section` for the first of `keys` present, else its `default` (a list of words or one word)."""
+    sec = d.get(section, {})
+    for k in keys + ("default",):
+        if k in sec:
+            v = sec[k]
+            return " ".join(str(w) for w in v) if isinstance(v, list) else str(v)
+    return None
+
+
+def _check_schemes(case_dir):
+    """The kernels hard-code the schemes every shipped case selects (tutorials/*/system/fvSchemes:18-47): Euler or backward ddt
+    (thermoScheme.H:41-49), Gauss harmonic for laplacian(kappa,T), linear interpolation (setDeltaT.H:21-27).  Anything else is
+    refused instead of being approximated."""
+    path = os.path.join(case_dir, "system", "fvSchemes")
+    if not os.path.exists(path):
+        raise FoamCaseError("system/fvSchemes is missing")
+    d = parse_dictionary(_read(case_dir, "system", "fvSchemes"))
+    ddt = _scheme(d, "ddtSchemes", "ddt(T)")
+    if ddt not in ("Euler",):
+        raise FoamCaseError(f"ddtSchemes {ddt!r}: read_case wires the Euler scheme only (backward is available through the case "
+                            "description's controls['ddtScheme']; CrankNicolson is not implemented)")
+    # `laplacian(kappa,T)` is one word to OpenFOAM but a word plus a list to this module's grammar: look for it in the text itself
+    text = re.sub(r"//[^\n]*|/\*.*?\*/", "", _read(case_dir, "system", "fvSchemes"), flags=re.S)
+    m = re.search(r"laplacian\(\s*kappa\s*,\s*T\s*\)\s+([^;]+);", text)
+    lap = m.group(1).strip() if m else _scheme(d, "laplacianSchemes")
+    if lap is None or lap.split()[:2] != ["Gauss", "harmonic"]:
+        raise FoamCaseError(f"laplacianSchemes laplacian(kappa,T) {lap!r}: the assembly kernels implement Gauss harmonic")
+    interp = _scheme(d, "interpolationSchemes")
+    if interp != "linear":
+        raise FoamCaseError(f"interpolationSchemes default {interp!r}: the diffusion-number kernel implements linear interpolation")
 
 
 def _read_powder(case_dir, mesh):

@@ -24,11 +24,12 @@ dp, ip = abi.c_double_p, abi.c_int32_p
 #: every symbol include/additivefoam_b200.h declares
 SYMBOLS = [
     "b200_last_error", "b200_abi_version", "b200_nccl_unique_id", "b200_ctx_create", "b200_ctx_destroy",
-    "b200_ctx_peer_export", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
+    "b200_ctx_peer_export", "b200_ctx_peer_export_halo", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_mixed_temperature_value_fraction", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
-    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_sources_update", "b200_case_solidification_enable",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_set_field_async", "b200_case_apply_staged",
+    "b200_case_get_field_async", "b200_case_transfers_wait", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_sources_update", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse", "b200_create_scan_path",
 ]
@@ -77,6 +78,7 @@ def load():
     L.b200_ctx_synchronize.argtypes = [vp]
     L.b200_ctx_peer_export.argtypes = [vp, vp]
     L.b200_ctx_peer_import.argtypes = [vp, vp]
+    L.b200_ctx_peer_export_halo.argtypes = [vp, C.c_int64, vp]
     L.b200_ctx_mark.argtypes = [vp, C.c_int]
     L.b200_ctx_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, dp]
     L.b200_profile_enable.argtypes = [vp, C.c_int]
@@ -106,6 +108,10 @@ def load():
     L.b200_case_n_cells.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.b200_case_get_field.argtypes = [vp, C.c_int32, dp]
     L.b200_case_set_field.argtypes = [vp, C.c_int32, dp]
+    L.b200_case_set_field_async.argtypes = [vp, C.c_int32, dp]
+    L.b200_case_get_field_async.argtypes = [vp, C.c_int32, dp]
+    L.b200_case_apply_staged.argtypes = [vp]
+    L.b200_case_transfers_wait.argtypes = [vp]
     L.b200_case_melt_pool_dimensions.argtypes = [vp, C.c_int32, dp, C.c_double, dp]
     L.b200_case_isotherm_depth.argtypes = [vp, C.c_int32, dp, dp]
     L.b200_case_sources_update.argtypes = [vp, C.c_double, dp]
@@ -158,10 +164,14 @@ class Context:
     def synchronize(self):
         _check(self.L.b200_ctx_synchronize(self.h))
 
-    def peer_export(self):
-        """64-byte IPC handle of this rank's all-reduce mailbox."""
+    def peer_export(self, halo_doubles=0):
+        """64-byte IPC handle of this rank's all-reduce mailbox; with `halo_doubles` > 0 the allocation also carries the window
+        the slab neighbours store their halo planes into (>= nx*ny of the largest case on this context)."""
         buf = (C.c_char * 64)()
-        _check(self.L.b200_ctx_peer_export(self.h, buf))
+        if halo_doubles > 0:
+            _check(self.L.b200_ctx_peer_export_halo(self.h, int(halo_doubles), buf))
+        else:
+            _check(self.L.b200_ctx_peer_export(self.h, buf))
         return bytes(buf)
 
     def peer_import(self, handles):
@@ -340,6 +350,21 @@ class Case:
     def set_field_keep_old(self, f, a):
         """set_field without touching the old-time copy (host application owns the field between steps)."""
         _check(self.L.b200_case_set_field(self.h, f | 0x100, _P(a)))
+
+    def set_field_async(self, f, pinned):
+        """Streamed upload from PINNED host memory (see include/additivefoam_b200.h); takes effect at apply_staged()."""
+        assert pinned.size == self.n_local and pinned.dtype == np.float64
+        _check(self.L.b200_case_set_field_async(self.h, f, _P(pinned)))
+
+    def apply_staged(self):
+        _check(self.L.b200_case_apply_staged(self.h))
+
+    def get_field_async(self, f, pinned_out):
+        assert pinned_out.size == self.n_local and pinned_out.dtype == np.float64
+        _check(self.L.b200_case_get_field_async(self.h, f, _P(pinned_out)))
+
+    def transfers_wait(self):
+        _check(self.L.b200_case_transfers_wait(self.h))
 
     def melt_pool_dimensions(self, iso_values, angle_deg=0.0):
         """meltPoolDimensions function object (meltPoolDimensions.C:123-294): (nIso, 3) spans, computed on the device."""

@@ -47,14 +47,19 @@ def max_over_ranks(value, dist, device=None):
     return float(t.item())
 
 
-def enable_peer_allreduce(ctx, dist, device=None):
-    """All ranks of one node: exchange the IPC handles of the all-reduce mailboxes and switch the library's scalar
-    all-reduces from NCCL to the NVLink peer-memory exchange."""
+def enable_peer(ctx, dist, device=None, halo_doubles=0):
+    """All ranks of one node: exchange the IPC handles of the peer mailboxes and switch the library's scalar all-reduces -- and,
+    with `halo_doubles` >= nx*ny, its halo-plane exchanges -- from NCCL to stores into peer memory over NVLink."""
     import torch
-    mine = torch.tensor(list(ctx.peer_export()), dtype=torch.uint8, device=device)
+    mine = torch.tensor(list(ctx.peer_export(halo_doubles)), dtype=torch.uint8, device=device)
     out = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(ctx.nranks)]
     dist.all_gather(out, mine)
     ctx.peer_import(b"".join(bytes(o.cpu().tolist()) for o in out))
+
+
+def enable_peer_allreduce(ctx, dist, device=None):
+    """The all-reduce mailbox only (halo planes stay on ncclSend/ncclRecv)."""
+    enable_peer(ctx, dist, device=device, halo_doubles=0)
 
 
 def decompose_ldu(n_cells, lower, upper, diag, upper_coeffs, lower_coeffs, rank, nranks):

@@ -8,9 +8,11 @@ A "step" is one full pass of additiveFoam's time-loop body (additiveFoam.C:66-95
 properties, time-step control, moving heat source, TEqn assembly, every solidification corrector and every
 Krylov iteration.  Workload: BASELINE.json configs[2] -- the synthetic 100 M-cell uniform-hex block (1000 x 400 x 250 cells of 20 um),
 single superGaussian track, conduction + solidification, implicit PCG/DIC with the shipped solver controls (tolerance
-1e-15, maxIter 20).  It fits one B200 (about 32 GB), so N = 1 runs exactly that case; N GPUs run N such z-slabs
-(weak scaling, 1000 x 400 x 250N cells).  `--nz-per-gpu 32` gives the thin-slab variant whose N = 8 run is the
-102.4 M-cell case of the BASELINE target (12.8 M cells per GPU).
+1e-15, maxIter 20), "decomposed 1/2/4/8": the SAME 100 M-cell mesh is cut into N z-slabs, one per GPU (strong scaling; the
+reference decomposes one case over its MPI ranks the same way, tutorials/AMB2018-02-B/system/decomposeParDict:18-20).  The
+weak-scaled number (N slabs of 100 M cells each) is carried as the sub-record `weak`.  `--impl reference` runs the same global
+mesh on the host cores.  With N > 1 a small decomposed case is first checked against the oracle's emulation of the same N
+ranks (`parity_check` on the JSON line).
 Prints ONE JSON line.
 """
 import argparse
@@ -36,7 +38,11 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--nx", type=int, default=1000)
     ap.add_argument("--ny", type=int, default=400)
-    ap.add_argument("--nz-per-gpu", type=int, default=250)
+    ap.add_argument("--nz", type=int, default=250, help="z layers of the global mesh (strong scaling: cut into --gpus slabs)")
+    ap.add_argument("--nz-per-gpu", type=int, default=250, help="z layers per GPU of the weak-scaled run")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaled sub-record (N > 1, --scaling strong)")
+    ap.add_argument("--no-parity-check", action="store_true")
     ap.add_argument("--workload", default="track", choices=["track", "rosenthal"])
     ap.add_argument("--explicit", action="store_true", help="as-shipped mode of configs[0]: explicitSolve true, maxDi 1 (diagonal solves only)")
     ap.add_argument("--solver", default="PCG", choices=["PCG", "PBiCGStab"])
@@ -44,7 +50,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-sample-nz", type=int, default=0, help="z layers of the CPU sample (0 = auto)")
-    ap.add_argument("--cpu-steps", type=int, default=16)
+    ap.add_argument("--cpu-steps", type=int, default=4)
     return ap.parse_args()
 
 
@@ -66,8 +72,11 @@ def workload_name(args, nz):
     if args.explicit:
         kind += ", explicitSolve true / maxDi 1 (as-shipped mode)"
     return (f"synthetic uniform-hex {args.nx}x{args.ny}x{nz} cells (20 um), single superGaussian beam, {kind}, implicit "
-            f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20 (BASELINE configs[2]: 100 M cells per GPU slab of "
-            f"{args.nz_per_gpu} z-layers; weak scaling over z-slabs)")
+            f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20 (BASELINE configs[2])")
+
+
+def global_nz(args, world):
+    return args.nz if args.scaling == "strong" else args.nz_per_gpu * world
 
 
 class ClockSampler(threading.Thread):
@@ -124,22 +133,35 @@ def run_cpu(args, nz, steps, warmup, ranks):
     dt = time.perf_counter() - t0
     n = o.n
     o.close()
-    return dict(value=n * steps / dt, seconds=dt, cells=n, iterations=iters, steps=steps)
+    return dict(value=n * steps / dt, seconds=dt, cells=n, iterations=iters, steps=steps, cell_iterations_per_s=n * iters / dt)
+
+
+def source_hash():
+    """sha256 over the CUDA sources the library is built from: ties an ncu capture to the build it was taken on."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "additivefoam_b200", "csrc", "*.cu*"))):
+        h.update(os.path.basename(f).encode())
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
 
 
 def ncu_traffic(group, n_local):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's kernel from the committed ncu --set full capture of
-    this command (profiles/r1_top_kernels_ncu_full_<cells>.csv); None for sizes or groups that were not captured."""
-    tag = {"sweep_fwd": "k_wave2<1,", "sweep_bwd": "k_wave2<2,", "factor": "k_wave2<0,", "amul": "k_amul_block<2>"}.get(group)
-    path = os.path.join(ROOT, "profiles", f"r1_top_kernels_ncu_full_{n_local}.csv")
-    if tag is None or not os.path.exists(path):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the group's kernel, from profiles/r2_traffic.json -- written by
+    tools/summarize_ncu.py from an `ncu --set full` capture of this command, together with the hash of the CUDA sources it was
+    taken on.  Another build (any kernel source changed since) or a size that was not captured gives None: a stale number is
+    worse than none."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
         return None
-    import csv
-    rows = list(csv.reader(open(path)))
-    hdr = rows[0]
-    vals = [float(r[hdr.index("dram_read_bytes")]) + float(r[hdr.index("dram_write_bytes")]) for r in rows[1:] if r and tag in r[0]]
-    vals = [v for v in vals if v > 1e6]       # the exact factor sweep behind the fast one returns at once: not a real launch
-    return sum(vals) / len(vals) if vals else None
+    try:
+        t = json.load(open(path))
+    except Exception:
+        return None
+    if t.get("source_hash") != source_hash():
+        return None
+    return t.get("bytes_per_launch", {}).get(str(n_local), {}).get(group)
 
 
 def peak_hbm():
@@ -152,6 +174,120 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def available_host_bytes():
+    try:
+        import psutil
+        return int(psutil.virtual_memory().available)
+    except Exception:
+        return None
+
+
+ORACLE_BYTES_PER_CELL = 360      # measured: 345 B/cell resident at 6.4 M cells (fields, LDU matrix and addressing, Krylov vectors)
+
+
+def reference_arm(args, N):
+    """The reference algorithm on the host cores, on the SAME global mesh as the GPU arm: every step is a full time step of the
+    whole block.  Sub-domains are compact z-slabs, one per core (at least 4 layers thick), each with block-local DIC -- the way an
+    `mpirun -np <cores> additiveFoam -parallel` run is decomposed (decomposeParDict:18-20)."""
+    cores = host_cores()
+    nz = global_nz(args, N)
+    ranks = max(1, min(cores, nz // 4 if nz >= 4 else 1))
+    note = ""
+    avail = available_host_bytes()
+    need = ORACLE_BYTES_PER_CELL * args.nx * args.ny * nz
+    if args.cpu_sample_nz:
+        nz_run = args.cpu_sample_nz
+    elif avail is not None and need > 0.8 * avail:
+        nz_run = max(4 * ranks, int(0.8 * avail / (ORACLE_BYTES_PER_CELL * args.nx * args.ny)))
+        note = f"; host memory ({avail / 2**30:.0f} GiB free) holds only {nz_run} of the {nz} z layers"
+    else:
+        nz_run = nz
+    ranks = max(1, min(ranks, nz_run // 4 if nz_run >= 4 else 1))
+    r = run_cpu(args, nz_run, args.steps, args.warmup, ranks)
+    full = nz_run == nz
+    sample = (f"{'the full mesh' if full else 'a sub-slab'}: {args.nx}x{args.ny}x{nz_run} cells, {args.steps} time steps after {args.warmup} warm-up, "
+              f"{ranks} compact z-slab sub-domains of ~{nz_run / ranks:.1f} layers on {ranks} threads, {r['seconds']:.1f} s{note}")
+    return {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": N, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": args.scaling,
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, nz), "cells": r["cells"], "krylov_iterations": r["iterations"],
+                       "cell_iterations_per_s": r["cell_iterations_per_s"], "same_mesh_as_gpu_arm": full,
+                       "note": "restatement of the reference algorithm (CPU oracle, OpenMP over z-slab ranks), not the OpenFOAM "
+                               "binary: OpenFOAM-10 is not installable here"},
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": ranks, "kind": "port", "sample": sample},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def parity_check(ctx, dist, rank, world):
+    """A small case decomposed over the SAME ranks, 12 time steps, against the oracle's in-process emulation of `world` ranks
+    (rank 0 runs the oracle).  Puts multi-GPU parity on the bench line, where the driver's SCALE run can see it."""
+    import numpy as np
+    from additivefoam_b200 import abi, cases, lib, partition
+    n = (60, 16, max(12, 3 * world))
+    case = cases.amb2018_02_b(n=n, explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC)
+    g = lib.Case(ctx, case)
+    reps = [g.step() for _ in range(12)]
+    T = partition.gather_field(g.field(abi.FIELD_T), n, rank, world, dist, device="cuda")
+    A = partition.gather_field(g.field(abi.FIELD_ALPHA_SOLID), n, rank, world, dist, device="cuda")
+    g.close()
+    out = None
+    if rank == 0:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as ol
+        o = ol.OracleCase(case, ranks=world)
+        oreps = [o.step() for _ in range(12)]
+        To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
+        eT = float(np.max(np.abs(T - To)) / np.max(np.abs(To)))
+        eA = float(np.max(np.abs(A - Ao)))
+        its = max(abs(a.lastSolveIterations - b.lastSolveIterations) for a, b in zip(reps, oreps))
+        corr = max(abs(a.nThermoCorr - b.nThermoCorr) for a, b in zip(reps, oreps))
+        o.close()
+        out = {"ranks": world, "case": f"AMB2018-02-B {n[0]}x{n[1]}x{n[2]} implicit PCG/DIC, 12 steps, vs the oracle's {world}-rank emulation",
+               "relLinf_T": eT, "Linf_alpha": eA, "iter_diff": its, "corrector_diff": corr, "Tmax": float(To.max()),
+               "ok": bool(eT < 1e-9 and eA < 1e-9 and its <= 1 and corr == 0)}
+    return out
+
+
+def timed_run(args, ctx, dist, torch, world, nz, steps, warmup, profile):
+    """W warm-up + K timed steps of the case with `nz` global layers; device-timed, max over ranks."""
+    from additivefoam_b200 import lib
+    case = make_case(args, nz)
+    g = lib.Case(ctx, case)
+
+    def barrier():
+        ctx.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        g.step()
+    barrier()
+    if profile:
+        ctx.profile_enable(True)
+    launches0 = ctx.kernel_launches()
+    ctx.mark(0)
+    iters = correctors = 0
+    last = None
+    for _ in range(steps):
+        last = g.step()
+        iters += last.nSolveIterations
+        correctors += last.nThermoCorr
+    ctx.mark(1)
+    ms = ctx.elapsed_ms(0, 1)
+    barrier()
+    launches = ctx.kernel_launches() - launches0
+    prof = None
+    if profile:
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    return dict(case=case, g=g, ms=ms, iters=iters, correctors=correctors, last=last, launches=launches, prof=prof, barrier=barrier)
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -162,19 +298,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        cores = host_cores()
-        nz = args.cpu_sample_nz or max(8, min(cores, args.nz_per_gpu))
-        ranks = min(cores, nz)
-        r = run_cpu(args, nz, args.steps, args.warmup, ranks)
-        sample = f"{args.nx}x{args.ny}x{nz} cells of the per-GPU slab, {args.steps} steps after {args.warmup} warm-up, {ranks} z-slab ranks"
-        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": N, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(args, args.nz_per_gpu * N), "note": "restatement of the reference algorithm "
-                           "(CPU oracle, OpenMP over z-slab ranks), not the OpenFOAM binary: OpenFOAM-10 is not installable here"},
-                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": ranks, "kind": "port", "sample": sample},
-                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(reference_arm(args, N)))
         return 0
 
     os.environ.setdefault("NCCL_DEBUG", "WARN")       # keep stdout to the one JSON line
@@ -183,6 +307,7 @@ def main():
     from additivefoam_b200 import abi, lib
 
     uid = None
+    dist = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -195,84 +320,49 @@ def main():
     ctx = lib.Context(local, uid, rank, world)
     if world > 1 and os.environ.get("B200_PEER_ALLREDUCE", "1") != "0":
         from additivefoam_b200 import partition
-        partition.enable_peer_allreduce(ctx, dist, device="cuda")
-    nz = args.nz_per_gpu * world
-    case = make_case(args, nz)
-    g = lib.Case(ctx, case)
-    n_global = g.n_global
+        partition.enable_peer(ctx, dist, device="cuda", halo_doubles=args.nx * args.ny)
 
-    def barrier():
-        ctx.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+    parity = None
+    if world > 1 and not args.no_parity_check:
+        parity = parity_check(ctx, dist, rank, world)
 
-    for _ in range(args.warmup):
-        g.step()
-    barrier()
+    nz = global_nz(args, world)
     sampler = ClockSampler(local)
     sampler.start()
-    ctx.profile_enable(True)
-    launches0 = ctx.kernel_launches()
-    ctx.mark(0)
-    iters = correctors = 0
-    last = None
-    for _ in range(args.steps):
-        last = g.step()
-        iters += last.nSolveIterations
-        correctors += last.nThermoCorr
-    ctx.mark(1)
-    ms = ctx.elapsed_ms(0, 1)
-    barrier()
-    launches = ctx.kernel_launches() - launches0
-    prof = ctx.profile_read()
-    ctx.profile_enable(False)
+    run = timed_run(args, ctx, dist, torch, world, nz, args.steps, args.warmup, profile=True)
     sampler.stop_flag.set()
     sampler.join(2)
-    if world > 1:
-        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ms = float(tm.item())
+    g, ms, iters, correctors, last, prof = run["g"], run["ms"], run["iters"], run["correctors"], run["last"], run["prof"]
+    barrier = run["barrier"]
+    n_global = g.n_global
     value = n_global * args.steps / (ms * 1e-3)
 
-    # ---- end to end through the C ABI with HOST fields: every step T/alpha.solid/alpha.powder go host -> device and
-    # T/alpha.solid come back (a host application that owns the fields, e.g. OpenFOAM function objects reading T)
+    # ---- end to end through the C ABI with HOST fields (see e2e_run)
     e2e = None
     if not args.no_e2e:
-        nl = g.n_local
-        hT = torch.from_numpy(g.field(abi.FIELD_T)).pin_memory().numpy()
-        hA = torch.from_numpy(g.field(abi.FIELD_ALPHA_SOLID)).pin_memory().numpy()
-        hP = torch.from_numpy(g.field(abi.FIELD_ALPHA_POWDER)).pin_memory().numpy()
-        e_steps = max(2, args.steps // 2)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e_steps):
-            g.set_field(abi.FIELD_ALPHA_POWDER, hP)
-            g.set_field_keep_old(abi.FIELD_T, hT)
-            g.set_field_keep_old(abi.FIELD_ALPHA_SOLID, hA)
-            g.step()
-            g.field_into(abi.FIELD_T, hT)
-            g.field_into(abi.FIELD_ALPHA_SOLID, hA)
-        barrier()
-        et = time.perf_counter() - t0
-        if world > 1:
-            tm = torch.tensor([et], dtype=torch.float64, device="cuda")
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            et = float(tm.item())
-        e2e = {"value": n_global * e_steps / et, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * nl * world,
-               "d2h_bytes_per_step": 2 * 8 * nl * world, "steps": e_steps,
-               "what": "b200_case_set_field(T, alpha.solid, alpha.powder) from pinned host + b200_case_step + b200_case_get_field(T, alpha.solid)"}
+        e2e = e2e_run(args, g, abi, torch, dist, world, barrier, n_global)
+    nl = g.n_local
+    nzl = nl // (args.nx * args.ny)
+    g.close()
+
+    # ---- the weak-scaled companion number (N slabs of --nz-per-gpu layers each), fewer steps
+    weak = None
+    if world > 1 and args.scaling == "strong" and not args.no_weak:
+        wsteps, wwarm = min(args.steps, 8), min(args.warmup, 3)
+        wr = timed_run(args, ctx, dist, torch, world, args.nz_per_gpu * world, wsteps, wwarm, profile=False)
+        wn = wr["g"].n_global
+        weak = {"value": wn * wsteps / (wr["ms"] * 1e-3), "unit": UNIT, "cells": wn, "ms_per_step": wr["ms"] / wsteps, "steps": wsteps,
+                "warmup": wwarm, "what": f"{world} z-slabs of {args.nx}x{args.ny}x{args.nz_per_gpu} cells (weak scaling)"}
+        wr["g"].close()
 
     if rank != 0:
-        g.close(); ctx.close()
+        ctx.close()
         dist.barrier()
         dist.destroy_process_group()
         return 0
 
     # ---- roofline of the dominant kernel group (CUDA events around every launch, live in this run)
-    nl = g.n_local
-    d = case["mesh"]["n"]
-    nzl = nz // world
+    d = run["case"]["mesh"]["n"]
     nf = (d[0] - 1) * d[1] * nzl + d[0] * (d[1] - 1) * nzl + d[0] * d[1] * (nzl - 1)
     alg_bytes = {  # SURVEY.md 8(d), per launch
         "amul": 24 * nl + 16 * nf, "sweep_fwd": 24 * nl + 16 * nf, "sweep_bwd": 24 * nl + 16 * nf, "factor": 16 * nl + 16 * nf,
@@ -289,37 +379,103 @@ def main():
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes[dom],
                 "avg_launch_ms": per_launch_ms[dom], "launches": prof[dom][1], "share_of_kernel_time": shares.get(dom),
                 "group_shares": shares,
+                "group_ms_per_launch": {k: round(v, 4) for k, v in per_launch_ms.items()},
                 "group_GBps": {k: round(alg_bytes[k] / (per_launch_ms[k] * 1e-3) / 1e9, 1) for k in per_launch_ms if alg_bytes.get(k)},
                 "note": "achieved = SURVEY.md 8(d) algorithmic bytes (general LDU addressing: 72 B/cell for Amul and for each sweep) / "
                         "measured launch time; the block path moves less (Amul 48, forward sweep 56, backward sweep 64 B/cell: no "
-                        "addressing arrays, see DESIGN.md section 5), so compare `traffic` / avg_launch_ms with the peak for the DRAM rate"}
+                        "addressing arrays, see DESIGN.md section 5), so compare `traffic` / avg_launch_ms with the peak for the DRAM rate; "
+                        "traffic is null unless profiles/r2_traffic.json was captured on this very build"}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         cores = host_cores()
-        cnz = args.cpu_sample_nz or max(8, min(cores, args.nz_per_gpu))
-        ranks = min(cores, cnz)
+        ranks = max(1, min(cores, nz // 4))
+        cnz = args.cpu_sample_nz or min(nz, 4 * ranks)
         try:
-            r = run_cpu(args, cnz, args.cpu_steps, args.warmup, ranks)
+            r = run_cpu(args, cnz, args.cpu_steps, 2, ranks)
             cpu = {"value": r["value"], "unit": UNIT, "cores": ranks, "kind": "port",
-                   "sample": f"{args.nx}x{args.ny}x{cnz} cells ({cnz}/{args.nz_per_gpu} of the slab), {args.cpu_steps} steps after {args.warmup} warm-up, "
-                             f"{r['seconds']:.1f} s; restatement of the reference algorithm, not the OpenFOAM binary"}
+                   "sample": f"{args.nx}x{args.ny}x{cnz} cells ({cnz}/{nz} of the mesh), {args.cpu_steps} steps after 2 warm-up, {ranks} compact z-slab "
+                             f"sub-domains, {r['seconds']:.1f} s; restatement of the reference algorithm, not the OpenFOAM binary "
+                             "(`--impl reference` times the full mesh)"}
         except Exception as e:     # the oracle is only the reported baseline
             cpu = {"value": None, "unit": UNIT, "cores": ranks, "kind": "port", "sample": f"failed: {e}"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args, nz), "cells": n_global, "krylov_iterations": iters, "correctors": correctors,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, nz), "cells": n_global, "cells_per_gpu": nl, "decomposition": f"{world} z-slab(s)",
+                       "krylov_iterations": iters, "correctors": correctors,
                        "cell_iterations_per_s": n_global * iters / (ms * 1e-3), "l2": "inputs larger than L2 (>= 100 MB per field)",
                        "last_step": last.as_dict()},
-            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu}
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": run["launches"], "roofline": roofline, "cpu_baseline": cpu}
+    if weak is not None:
+        line["weak"] = weak
+    if parity is not None:
+        line["parity_check"] = parity
     print(json.dumps(line), flush=True)
-    g.close(); ctx.close()
+    ctx.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def e2e_run(args, g, abi, torch, dist, world, barrier, n_global):
+    """The same metric through the C ABI with HOST buffers.  Two figures:
+
+    * `value` (streamed): a host application that feeds the step and consumes its result without waiting on either -- the inputs
+      of step n+1 (T, alpha.solid, alpha.powder; pinned host memory) cross PCIe on a copy stream while step n computes, and the
+      results of step n (T, alpha.solid) go back on a second copy stream while step n+1 computes
+      (b200_case_set_field_async / get_field_async / transfers_wait).  Every step's inputs and results cross PCIe inside the timed region.
+    * `serial`: the same bytes with the strict dependency upload -> step -> download (b200_case_set_field / step / get_field),
+      i.e. a host that edits the fields between steps."""
+    nl = g.n_local
+    hT = torch.from_numpy(g.field(abi.FIELD_T)).pin_memory().numpy()
+    hA = torch.from_numpy(g.field(abi.FIELD_ALPHA_SOLID)).pin_memory().numpy()
+    hP = torch.from_numpy(g.field(abi.FIELD_ALPHA_POWDER)).pin_memory().numpy()
+    oT = [torch.empty(nl, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    oA = [torch.empty(nl, dtype=torch.float64).pin_memory().numpy() for _ in range(2)]
+    e_steps = max(2, args.steps // 2)
+
+    def reduce_max(x):
+        if world > 1:
+            tm = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return float(tm.item())
+        return x
+
+    # serial
+    s_steps = max(2, e_steps // 2)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(s_steps):
+        g.set_field(abi.FIELD_ALPHA_POWDER, hP)
+        g.set_field_keep_old(abi.FIELD_T, hT)
+        g.set_field_keep_old(abi.FIELD_ALPHA_SOLID, hA)
+        g.step()
+        g.field_into(abi.FIELD_T, hT)
+        g.field_into(abi.FIELD_ALPHA_SOLID, hA)
+    barrier()
+    st = reduce_max(time.perf_counter() - t0)
+    # streamed
+    barrier()
+    t0 = time.perf_counter()
+    g.set_field_async(abi.FIELD_ALPHA_POWDER, hP); g.set_field_async(abi.FIELD_T, hT); g.set_field_async(abi.FIELD_ALPHA_SOLID, hA)
+    for i in range(e_steps):
+        g.apply_staged()                       # the staged inputs become the step's fields (device-to-device)
+        if i + 1 < e_steps:                    # next step's inputs start crossing now, under this step's kernels
+            g.set_field_async(abi.FIELD_ALPHA_POWDER, hP); g.set_field_async(abi.FIELD_T, hT); g.set_field_async(abi.FIELD_ALPHA_SOLID, hA)
+        g.step()
+        g.get_field_async(abi.FIELD_T, oT[i & 1]); g.get_field_async(abi.FIELD_ALPHA_SOLID, oA[i & 1])
+    g.transfers_wait()
+    barrier()
+    et = reduce_max(time.perf_counter() - t0)
+    return {"value": n_global * e_steps / et, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * nl * world,
+            "d2h_bytes_per_step": 2 * 8 * nl * world, "steps": e_steps,
+            "what": "streamed: b200_case_set_field_async(T, alpha.solid, alpha.powder) of step n+1 from pinned host memory under step n, "
+                    "b200_case_step, b200_case_get_field_async(T, alpha.solid) of step n under step n+1; all copies inside the timed region",
+            "serial": {"value": n_global * s_steps / st, "steps": s_steps,
+                       "what": "b200_case_set_field x3 -> b200_case_step -> b200_case_get_field x2, each blocking"}}
 
 
 if __name__ == "__main__":

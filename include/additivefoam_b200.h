@@ -54,6 +54,9 @@ enum {
     B200_FIELD_T = 0, B200_FIELD_ALPHA_SOLID = 1, B200_FIELD_ALPHA_POWDER = 2,
     B200_FIELD_KAPPA = 3, B200_FIELD_CP = 4, B200_FIELD_QDOT = 5,
     B200_FIELD_DFDT = 6, B200_FIELD_T0 = 7,
+    /* old-time copies (T.oldTime(), alpha.solid.oldTime(); [UPSTREAM] GeometricField::storeOldTimes at runTime++,
+     * additiveFoam.C:76): plain upload / download, for restarts and for resynchronising a run with another one */
+    B200_FIELD_T_OLD = 8, B200_FIELD_ALPHA_SOLID_OLD = 9,
     /* OR-ed into the field id of b200_case_set_field: upload only, leave the old-time copy and the patch state alone
      * (a host application that owns the field between steps re-uploads the same values) */
     B200_FIELD_KEEP_OLD = 0x100
@@ -177,6 +180,11 @@ int  b200_ctx_destroy(b200_ctx* ctx);
  * Every rank exports a 64-byte cudaIpcMemHandle_t, the host gathers them in rank order, every rank imports the list. */
 int  b200_ctx_peer_export(b200_ctx* ctx, void* handle64);
 int  b200_ctx_peer_import(b200_ctx* ctx, const void* handles /* nranks x 64 bytes */);
+/* Same export, with a halo window of 4 x haloDoubles doubles behind the mailbox: the slab neighbours then store their boundary
+ * planes (processor-patch halo swaps: [UPSTREAM] processorFvPatchField::initEvaluate / initInterfaceMatrixUpdate) straight into
+ * it over NVLink -- one kernel per exchange, no NCCL call.  haloDoubles >= nx*ny of the largest case run on this context; a
+ * larger plane falls back to ncclSend/ncclRecv. */
+int  b200_ctx_peer_export_halo(b200_ctx* ctx, int64_t haloDoubles, void* handle64);
 int  b200_ctx_synchronize(b200_ctx* ctx);
 /* CUDA events on the library's own stream (bench.py times the step with these): record mark i (0..3);
  * elapsed ms between two recorded marks (synchronises). */
@@ -259,6 +267,18 @@ int  b200_case_step(b200_case* c, b200_step_report* report);
 int  b200_case_n_cells(b200_case* c, int64_t* nLocal, int64_t* nGlobal);
 int  b200_case_get_field(b200_case* c, int32_t field, double* out);
 int  b200_case_set_field(b200_case* c, int32_t field, const double* in);
+/* Streamed host I/O for an application that feeds the step and consumes its result without waiting on either (e.g. a solver
+ * application whose function objects read T every step in their `execute()`).  Host buffers must be pinned.
+ *   set_field_async : host -> a device staging buffer on a copy stream of its own; returns at once.
+ *   apply_staged    : everything staged becomes the field (device-to-device, upload-only semantics of B200_FIELD_KEEP_OLD).
+ *   get_field_async : snapshot of the field, then device -> host on a second copy stream; returns at once.
+ *   transfers_wait  : both copy streams and the compute stream have drained; the host buffers hold the snapshots.
+ * Typical loop: set_field_async(inputs of step 0); for n: apply_staged; set_field_async(inputs of step n+1); step;
+ * get_field_async(results of step n).  The copies of step n+1 / step n then run under the kernels of step n / n+1. */
+int  b200_case_set_field_async(b200_case* c, int32_t field, const double* pinnedIn);
+int  b200_case_apply_staged(b200_case* c);
+int  b200_case_get_field_async(b200_case* c, int32_t field, double* pinnedOut);
+int  b200_case_transfers_wait(b200_case* c);
 /* functionObjects/meltPoolDimensions/meltPoolDimensions.C:123-294 evaluated on the device-resident T (no D2H of the field):
  * for each isoValue the bounding box, in the frame rotated about z by scanPathAngle (degrees), of the isotherm located linearly
  * between cell centres across internal and processor faces plus the centres of physical boundary faces whose cell or patch value

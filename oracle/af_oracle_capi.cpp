@@ -204,6 +204,8 @@ static Field* fieldOf(RankState& s, int f)
     case B200_FIELD_QDOT: return &s.qDot;
     case B200_FIELD_DFDT: return &s.dFdT;
     case B200_FIELD_T0: return &s.T0;
+    case B200_FIELD_T_OLD: return &s.Told;
+    case B200_FIELD_ALPHA_SOLID_OLD: return &s.alpha1old;
     }
     return nullptr;
 }

@@ -84,6 +84,14 @@ def write_case(root, explicit="false", solver="PCG", precond="DIC", powder=False
                 #endif
             }
             """),
+        "system/fvSchemes": HEADER + textwrap.dedent("""
+            ddtSchemes { default Euler; }
+            gradSchemes { default Gauss linear; }
+            divSchemes { default Gauss upwind; }
+            laplacianSchemes { default Gauss linear corrected; laplacian(kappa,T) Gauss harmonic corrected; }
+            interpolationSchemes { default linear; }
+            snGradSchemes { default corrected; }
+            """),
         "system/fvSolution": HEADER + textwrap.dedent(f"""
             solvers
             {{
@@ -165,6 +173,34 @@ def test_what_cannot_be_represented_is_refused(tmp_path):
     open(tpath, "w").write(ttext.replace("type zeroGradient;", "type codedFixedValue;"))
     with pytest.raises(foamcase.FoamCaseError, match="codedFixedValue"):
         foamcase.read_case(root)
+
+
+@pytest.mark.parametrize("rel,old,new,match", [
+    ("system/fvSolution", "nOuterCorrectors 0;", "nOuterCorrectors 1;", "nOuterCorrectors"),
+    ("system/fvSchemes", "default Euler;", "default CrankNicolson 0.9;", "ddtSchemes"),
+    ("system/fvSchemes", "default Euler;", "default backward;", "ddtSchemes"),
+    ("system/fvSchemes", "laplacian(kappa,T) Gauss harmonic corrected;", "", "laplacian"),
+    ("system/fvSchemes", "interpolationSchemes { default linear; }", "interpolationSchemes { default cubic; }", "interpolationSchemes"),
+])
+def test_schemes_and_flow_coupling_the_kernels_do_not_implement_are_refused(tmp_path, rel, old, new, match):
+    """a marangoni-style case (nOuterCorrectors 1, tutorials/verificationAndValidation/marangoni/system/fvSolution:48) or
+    a non-Euler / non-harmonic selection must raise instead of being run as Euler + harmonic pure conduction."""
+    root = write_case(tmp_path)
+    path = os.path.join(root, rel)
+    text = open(path).read()
+    assert old in text
+    open(path, "w").write(text.replace(old, new))
+    with pytest.raises(foamcase.FoamCaseError, match=match):
+        foamcase.read_case(root)
+
+
+@needs_reference
+def test_shipped_marangoni_case_is_refused():
+    root = os.path.join(TUT, "verificationAndValidation", "marangoni")
+    with pytest.raises(foamcase.FoamCaseError):           # (its one-cell-thick `empty` patch is refused before the controls are read)
+        foamcase.read_case(root)
+    with pytest.raises(foamcase.FoamCaseError, match="nOuterCorrectors"):
+        foamcase._read_controls(root)
 
 
 def _normalised(case):

@@ -20,39 +20,86 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 uid = partition.broadcast_unique_id(lib.nccl_unique_id, rank, dist, device="cuda")
 ctx = lib.Context(local, uid, rank, world)
 if os.environ.get("B200_PEER_ALLREDUCE", "1") != "0":
-    partition.enable_peer_allreduce(ctx, dist, device="cuda")
+    # B200_PEER_HALO=0: all-reduce mailbox only, halo planes over ncclSend/ncclRecv
+    partition.enable_peer(ctx, dist, device="cuda", halo_doubles=0 if os.environ.get("B200_PEER_HALO", "1") == "0" else 1 << 16)
 if mode == "fuzz":          # seeded random cases (tests/test_gpu_fuzz.py) decomposed over the ranks, against the oracle's emulation
     import test_gpu_fuzz as fz
+    import oracle_lib as ol
+    NSTEP = 20
+    seeds = [int(v) for v in os.environ["B200_FUZZ_SEEDS"].split(",")] if os.environ.get("B200_FUZZ_SEEDS") else list(range(steps))
+
+    def bcast(a, n_):
+        t = torch.zeros(n_, dtype=torch.float64, device="cuda")
+        if rank == 0:
+            t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
+        dist.broadcast(t, 0)
+        return t.cpu().numpy()
+
+    def run(case, resync):
+        """Per-step errors of the decomposed GPU run against the oracle's emulation of the same ranks.  resync: before every step
+        the GPU fields are overwritten with the oracle's, so the numbers are those of ONE time step from identical states."""
+        nn = case["mesh"]["n"]
+        ntot = nn[0] * nn[1] * nn[2]
+        k0, k1 = partition.slab_range(nn[2], rank, world)
+        sl = slice(nn[0] * nn[1] * k0, nn[0] * nn[1] * k1)
+        g = lib.Case(ctx, case)
+        o = ol.OracleCase(case, ranks=world) if rank == 0 else None
+        hist = []
+        for s_ in range(NSTEP):
+            if resync:
+                cur = {f: np.ascontiguousarray(bcast(o.field(f) if rank == 0 else None, ntot)[sl])
+                       for f in (abi.FIELD_ALPHA_POWDER, abi.FIELD_ALPHA_SOLID, abi.FIELD_T)}
+                g.set_field(abi.FIELD_T, cur[abi.FIELD_T])                      # also evaluates the patches, as the oracle's did
+                g.set_field(abi.FIELD_ALPHA_SOLID, cur[abi.FIELD_ALPHA_SOLID])
+                g.set_field(abi.FIELD_ALPHA_POWDER, cur[abi.FIELD_ALPHA_POWDER])
+                # T.oldTime() enters the thermo number of setDeltaT.H
+                g.set_field(abi.FIELD_T_OLD, np.ascontiguousarray(bcast(o.field(abi.FIELD_T_OLD) if rank == 0 else None, ntot)[sl]))
+            rg = g.step()
+            T = partition.gather_field(g.field(abi.FIELD_T), nn, rank, world, dist, device="cuda")
+            A = partition.gather_field(g.field(abi.FIELD_ALPHA_SOLID), nn, rank, world, dist, device="cuda")
+            if rank == 0:
+                ro = o.step()
+                To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
+                hist.append((float(np.max(np.abs(T - To)) / np.max(np.abs(To))), float(np.max(np.abs(A - Ao))),
+                             abs(rg.lastSolveIterations - ro.lastSolveIterations), abs(rg.nThermoCorr - ro.nThermoCorr)))
+        g.close()
+        if o is not None:
+            o.close()
+        return hist
+
     bad = []
-    for seed in range(steps):
+    for seed in seeds:
         case = fz.random_case(seed)
         if case["mesh"]["n"][2] < world:
             continue
-        g = lib.Case(ctx, case)
-        reps = [g.step() for _ in range(20)]
-        T = partition.gather_field(g.field(abi.FIELD_T), case["mesh"]["n"], rank, world, dist, device="cuda")
-        A = partition.gather_field(g.field(abi.FIELD_ALPHA_SOLID), case["mesh"]["n"], rank, world, dist, device="cuda")
-        g.close()
+        hist = run(case, False)
+        flag = torch.zeros(1, device="cuda")
         if rank == 0:
-            import oracle_lib as ol
-            o = ol.OracleCase(case, ranks=world)
-            oreps = [o.step() for _ in range(20)]
-            To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
-            eT, eA = float(np.max(np.abs(T - To)) / np.max(np.abs(To))), float(np.max(np.abs(A - Ao)))
-            its = max(abs(a.lastSolveIterations - b.lastSolveIterations) for a, b in zip(reps, oreps))
-            corr = max(abs(a.nThermoCorr - b.nThermoCorr) for a, b in zip(reps, oreps))
-            # bar: 1e-9 per time step; after 20 steps alpha.solid is allowed 1e-8 -- in the penalty branches of the corrector
-            # (thermoSource.H:51-60, slope 1e10) it magnifies differences of T that are themselves below 1e-10
-            if not (eT < 1e-9 and eA < 1e-8 and its <= 1 and corr == 0):
-                bad.append((seed, eT, eA, its, corr))
-            o.close()
+            eT, eA = max(h[0] for h in hist), max(h[1] for h in hist)
+            its, corr = max(h[2] for h in hist), max(h[3] for h in hist)
+            # bar (north star): 1e-9 at every time step on the states as they evolve, iteration counts within 1
+            good = eT < 1e-9 and eA < 1e-9 and its <= 1 and corr == 0
+            print(f"MULTI fuzz seed {seed}: max over {NSTEP} steps relLinf(T)={eT:.3e} Linf(alpha)={eA:.3e} iterdiff={its} corrdiff={corr} "
+                  f"{'ok' if good else 'EXCEEDS'}", flush=True)
+            flag[0] = 0 if good else 1
+        dist.broadcast(flag, 0)
+        if flag.item():
+            # the same seed once more, one step at a time from the oracle's state: separates an error made within a time step
+            # from the growth of an earlier difference (the corrector's penalty branches, thermoSource.H:51-60, have slope 1e10)
+            h2 = run(case, True)
+            if rank == 0:
+                print("  evolving states, per step (T, alpha): " + " ".join(f"({h[0]:.1e},{h[1]:.1e})" for h in hist), flush=True)
+                print("  one step from the oracle's state   : " + " ".join(f"({h[0]:.1e},{h[1]:.1e})" for h in h2), flush=True)
+                bad.append((seed, max(h[0] for h in hist), max(h[1] for h in hist), max(h[0] for h in h2), max(h[1] for h in h2)))
     ok = not bad
     if rank == 0:
-        print(f"MULTI fuzz ranks={world} seeds={steps} bad={bad} {'OK' if ok else 'FAIL'}", flush=True)
+        print(f"MULTI fuzz ranks={world} seeds={len(seeds)} peer_allreduce={os.environ.get('B200_PEER_ALLREDUCE', '1')} bad={bad} {'OK' if ok else 'FAIL'}", flush=True)
+    okt = torch.tensor([1.0 if ok else 0.0], device="cuda")
+    dist.broadcast(okt, 0)
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    sys.exit(0 if okt.item() else 1)
 n = (48, 14, 11)
 kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC) if mode == "implicit" else dict()
 if mode == "bicg":
