@@ -53,6 +53,41 @@ void Ctx::profRead(double* ms, int64_t* counts)
     for (int i = 0; i < PC_NCAT; i++) { if (ms) ms[i] = profMs[i]; if (counts) counts[i] = profCount[i]; profMs[i] = 0; profCount[i] = 0; }
 }
 
+void Ctx::profDropFrom(size_t firstRec, int firstDeadTag)
+{
+    size_t w = firstRec;
+    for (size_t r = firstRec; r < profRecs.size(); r++) {
+        if (profRecs[r].tag >= firstDeadTag) { profPool.push_back(profRecs[r].a); profPool.push_back(profRecs[r].b); }
+        else profRecs[w++] = profRecs[r];
+    }
+    profRecs.resize(w);
+}
+
+struct WordBlob { unsigned w[64]; };
+__global__ void k_words_to_host(unsigned* __restrict__ host, const unsigned* __restrict__ dev, int n)
+{
+    for (int i = threadIdx.x; i < n; i += 32) host[i] = dev[i];
+    __threadfence_system();
+}
+__global__ void k_words_to_device(unsigned* __restrict__ dev, WordBlob b, int n)
+{
+    for (int i = threadIdx.x; i < n; i += 32) dev[i] = b.w[i];
+}
+void words_to_host(Ctx* ctx, void* hostPinned, const void* dev, size_t bytes)
+{
+    B200_CHECK(bytes % 4 == 0, "words_to_host: size");
+    k_words_to_host<<<1, 32, 0, ctx->stream>>>((unsigned*)hostPinned, (const unsigned*)dev, (int)(bytes / 4));
+    B200_CUDA(cudaGetLastError());
+}
+void words_to_device(Ctx* ctx, void* dev, const void* host, size_t bytes)
+{
+    B200_CHECK(bytes % 4 == 0 && bytes <= sizeof(WordBlob), "words_to_device: size");
+    WordBlob b;
+    std::memcpy(b.w, host, bytes);
+    k_words_to_device<<<1, 32, 0, ctx->stream>>>((unsigned*)dev, b, (int)(bytes / 4));
+    B200_CUDA(cudaGetLastError());
+}
+
 Ctx::~Ctx()
 {
     for (auto& r : profRecs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -56,7 +56,10 @@ struct Ctx {
     void allreduceCtrl(double* red, int slot0, int n, int phase, SolveState* st);   // sum + the control step that consumes it, one kernel
     // profiler: one event pair per instrumented launch group, resolved at read time
     bool profOn = false;
-    struct ProfRec { int cat; cudaEvent_t a, b; };
+    struct ProfRec { int cat; cudaEvent_t a, b; int tag; };
+    int profTag = -1;              // Krylov iteration being enqueued (Ldu::solve); records of iterations that turn out to be past
+                                   // convergence -- kernels that return at once -- are dropped again (profDropFrom)
+    void profDropFrom(size_t firstRec, int firstDeadTag);
     std::vector<ProfRec> profRecs;
     std::vector<cudaEvent_t> profPool;
     double profMs[PC_NCAT] = {0};
@@ -92,11 +95,17 @@ struct ProfScope {
     {
         if (!c->profOn) return;
         cudaEvent_t a = c->profEvent(); b = c->profEvent();
-        c->profRecs.push_back({cat, a, b});
+        c->profRecs.push_back({cat, a, b, c->profTag});
         cudaEventRecord(a, c->stream);
     }
     ~ProfScope() { if (b) cudaEventRecord(b, c->stream); }
 };
+
+// A few words device -> PINNED host (or host-by-value -> device) written by a one-warp kernel instead of a DMA copy: the copy
+// engines serve transfers in order, so a tiny cudaMemcpyAsync of the step (solver state, reductions) would queue behind a
+// field-sized transfer of the streamed host I/O (b200_case_set_field_async / get_field_async) for tens of milliseconds.
+void words_to_host(Ctx* ctx, void* hostPinned, const void* dev, size_t bytes);      // bytes: multiple of 4, any size up to a few KB
+void words_to_device(Ctx* ctx, void* dev, const void* host, size_t bytes);          // bytes <= 256 (passed as a kernel argument)
 
 template <class T> inline T* dev_alloc(size_t n)
 {

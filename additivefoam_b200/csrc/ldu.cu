@@ -145,7 +145,7 @@ Ldu::~Ldu()
     for (auto& p : stage) dev_free(p);
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]);
     dev_free(d_fStart); dev_free(d_fPos); dev_free(d_fFace); dev_free(d_bStart); dev_free(d_bPos); dev_free(d_bFace);
     dev_free(flowCoefF); dev_free(flowCoefB); dev_free(flowNumF); dev_free(flowRD); dev_free(flowF); dev_free(flowB);
     dev_free(flowPartial); dev_free(flowTicket);
@@ -174,7 +174,7 @@ void Ldu::setBlock(int nx, int ny, int nz)
     dev_free(rD);
     // the wave-order arrays, the tile order and the gathered coefficients belong to the block shape
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]);
     waveEpoch = -1; waveUpper = nullptr; waveLower = nullptr;
 }
 
@@ -358,6 +358,20 @@ void Ldu::ensureWave(bool dilu)
         });
         waveOrder = dev_alloc<int>(g.nTiles);
         B200_CUDA(cudaMemcpyAsync(waveOrder, order.data(), sizeof(int) * g.nTiles, cudaMemcpyHostToDevice, ctx->stream));
+        // k_wave3: CTA tiles of NW tiles in J.  A J-hop between CTAs costs about NW tile lags, a K-hop one: hand out by 3*Jc + K
+        for (int q = 0; q < 2; q++) {
+            const int NW = q == 0 ? 4 : 2;
+            const int nJc = (g.nJ + NW - 1) / NW, nC = nJc * g.nK;
+            std::vector<int> oc(nC);
+            for (int t = 0; t < nC; t++) oc[t] = t;
+            static const int cJ = [] { const char* e = std::getenv("B200_WAVE3_ORDER_J"); return e ? std::atoi(e) : 3; }();
+            std::stable_sort(oc.begin(), oc.end(), [&](int x, int y) {
+                return (long)cJ * (x % nJc) + (x / nJc) < (long)cJ * (y % nJc) + (y / nJc);
+            });
+            waveOrderC[q] = dev_alloc<int>(nC);
+            B200_CUDA(cudaMemcpyAsync(waveOrderC[q], oc.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, ctx->stream));
+            B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
         B200_CUDA(cudaStreamSynchronize(ctx->stream));        // `order` is a local
     }
 }
@@ -387,7 +401,7 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.DG = wave[13];
     a.rA = rA; a.wA = wA;
     a.ticket = waveFlags; a.order = waveOrder; a.tilePartial = wavePartial; a.st = d_state;
-    a.trace = nullptr;
+    a.trace = nullptr; a.nCtas = 0; a.orderC = nullptr;
     static const bool traceOn = [] { const char* e = std::getenv("B200_WAVE_TRACE"); return e && std::atoi(e) != 0; }();
     if (traceOn) {
         if (!waveTrace) waveTrace = dev_alloc<long long>((size_t)a.g.nTiles * 12);
@@ -411,8 +425,12 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     // Two implementations of the same sweep (bit-identical results): the warp-specialised kernel (memory warp + compute warp
     // per tile) is the default at every size now that tiles are handed out along the wavefront; the one-warp kernel stays
     // selectable (B200_WAVE=1warp) as the reference point the profiles compare against.
-    const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : 2; }();
+    // B200_WAVE: "1warp" the one-warp kernel, "single" k_wave2 (one tile per CTA), "multi" k_wave3 (NW tiles per CTA); default:
+    // k_wave3 where the dependency chain across tiles bounds the sweep (few tiles: thin slabs, small blocks), k_wave2 where
+    // bandwidth does (thousands of tiles)
+    const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : std::string(e) == "multi" ? 3 : 2; }();
     const bool oneWarp = forced == 1;
+    const bool multi = forced == 3 || (forced == 0 && a.g.nTiles <= 1536);
     if (op == 0 && !oneWarp) {      // the warp-specialised factor sweep streams the diagonal from wave order as well
         k_wave_from_natural<<<waveVecGrid(), 256, 0, s>>>(a.g, rA, wave[13], 1.0, d_state); B200_LAUNCH_CHECK();
     }
@@ -422,6 +440,39 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         else if (wio) { if (dot) k_wave<2, false, true, true><<<grid, 32, 0, s>>>(a); else k_wave<2, false, false, true><<<grid, 32, 0, s>>>(a); }
         else if (dot) k_wave<2, false, true, false><<<grid, 32, 0, s>>>(a);
         else k_wave<2, false, false, false><<<grid, 32, 0, s>>>(a);
+    } else if (multi) {
+        // geometry by B200_WAVE3 = <NW><GSZ><RNG> (tiles per CTA, steps per ring slot, ring slots); default 4 x 4 x 6
+        const char* eg = std::getenv("B200_WAVE3");
+        const int cfg = eg ? std::atoi(eg) : 446;
+        const int NWsel = cfg / 100 == 2 ? 2 : 4;
+        a.nCtas = ((a.g.nJ + NWsel - 1) / NWsel) * a.g.nK;
+        a.orderC = waveOrderC[NWsel == 4 ? 0 : 1];
+        auto launch3 = [&](auto kernel, size_t shm, int threads) {
+            static std::set<const void*> configured;
+            if (configured.insert((const void*)kernel).second)
+                B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            kernel<<<a.nCtas, threads, shm, s>>>(a);
+        };
+#define B200_W3(G_, R_, RD_, N_)                                                                                                                \
+        do {                                                                                                                                   \
+            if (op == 0) { if (dilu) launch3(k_wave3<0, true, false, true, true, G_, RD_, N_>, sizeof(WaveSmem3<0, true, true, G_, RD_, N_>), 64 * N_);   \
+                           else launch3(k_wave3<0, false, false, true, true, G_, R_, N_>, sizeof(WaveSmem3<0, false, true, G_, R_, N_>), 64 * N_); }      \
+            else if (op == 1) { if (wio) launch3(k_wave3<1, false, false, true, false, G_, R_, N_>, sizeof(WaveSmem3<1, false, true, G_, R_, N_>), 64 * N_); \
+                                else launch3(k_wave3<1, false, false, false, false, G_, R_, N_>, sizeof(WaveSmem3<1, false, false, G_, R_, N_>), 64 * N_); } \
+            else if (wio) { if (dot) launch3(k_wave3<2, false, true, true, false, G_, R_, N_>, sizeof(WaveSmem3<2, false, true, G_, R_, N_>), 64 * N_);   \
+                            else launch3(k_wave3<2, false, false, true, false, G_, R_, N_>, sizeof(WaveSmem3<2, false, true, G_, R_, N_>), 64 * N_); }    \
+            else if (dot) launch3(k_wave3<2, false, true, false, false, G_, R_, N_>, sizeof(WaveSmem3<2, false, false, G_, R_, N_>), 64 * N_);            \
+            else launch3(k_wave3<2, false, false, false, false, G_, R_, N_>, sizeof(WaveSmem3<2, false, false, G_, R_, N_>), 64 * N_);                    \
+            if (op == 0) {                                                                                                                     \
+                k_wave_refactor_prepare<<<ctx->smCount * 4, 256, 0, s>>>(a, waveLen);                                                          \
+                if (dilu) launch3(k_wave3<0, true, false, true, false, G_, RD_, N_>, sizeof(WaveSmem3<0, true, true, G_, RD_, N_>), 64 * N_);             \
+                else launch3(k_wave3<0, false, false, true, false, G_, R_, N_>, sizeof(WaveSmem3<0, false, true, G_, R_, N_>), 64 * N_);                  \
+            }                                                                                                                                  \
+        } while (0)
+        if (cfg == 444) B200_W3(4, 4, 4, 4);
+        else if (cfg == 248) B200_W3(4, 8, 8, 2);
+        else B200_W3(4, 6, 5, 4);
+#undef B200_W3
     } else {
         auto launch = [&](auto kernel, size_t shm) {
             static std::set<const void*> configured;     // every k_wave2 instantiation has the same pointer type
@@ -654,7 +705,8 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     }
     const double nGlobal = nGlobalCells;
     h_state->nGlobal = nGlobal;
-    h2d(d_state, h_state, 1, s);
+    static_assert(sizeof(SolveState) <= 256 && sizeof(SolveState) % 4 == 0, "SolveState travels as a kernel argument");
+    words_to_device(ctx, d_state, h_state, sizeof(SolveState));
     const SolveState* st = d_state;
 
     const bool pcg = sc.solver == 0;
@@ -712,9 +764,11 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     // solves with the shipped controls all run to maxIter + 1) and the global cell count per rank.
     const bool large = nGlobalCells / ctx->nranks >= (double)(1 << 20);
     int enqueued = 0;
+    const size_t profFirst = ctx->profRecs.size();
     int chunk = lastIterations > 0 ? std::min(lastIterations, hardMax) : (large ? 1 : 2);
     for (;;) {
         for (int it = 0; it < chunk && enqueued < hardMax; it++, enqueued++) {
+            ctx->profTag = enqueued;
             if (pcg) {
                 applyPrecond(sc.precond, A, rA, wA, 1, rA, wio, C_PCG_BETA);    // wA = M^-1 rA ; wArA
                 reduceCtrl(S_RHO, 1, C_PCG_BETA);
@@ -747,7 +801,8 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
                 reduceCtrl(S_MAGR2, 1, C_ITER_END2);
             }
         }
-        d2h(h_state, d_state, 1, s);
+        ctx->profTag = -1;
+        words_to_host(ctx, h_state, d_state, sizeof(SolveState));
         ctx->sync();
         if (h_state->done || enqueued >= hardMax) break;
         chunk = large ? 1 : std::min(std::max(chunk, 1) * 2, 32);
@@ -755,6 +810,7 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     perf.initialResidual = h_state->initRes; perf.finalResidual = h_state->finalRes;
     perf.nIterations = h_state->nIter; perf.converged = h_state->converged; perf.singular = h_state->singular;
     lastIterations = perf.nIterations;
+    if (ctx->profOn) ctx->profDropFrom(profFirst, perf.nIterations);       // iterations enqueued past convergence were no-ops
     return perf;
 }
 

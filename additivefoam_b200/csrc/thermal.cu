@@ -343,7 +343,7 @@ void ThermalCase::meltPoolDimensions(int nIso, const double* isoValues, double s
         B200_LAUNCH_CHECK();
         ctx->allreduceMin(red.result + R_MPOOL, 3);
         ctx->allreduceMax(red.result + R_MPOOL + 3, 3);
-        d2h(h_red + R_MPOOL, red.result + R_MPOOL, 6, ctx->stream);
+        words_to_host(ctx, h_red + R_MPOOL, red.result + R_MPOOL, 6 * sizeof(double));
         ctx->sync();
         for (int a = 0; a < 3; a++) out[3 * q + a] = std::max(h_red[R_MPOOL + 3 + a] - h_red[R_MPOOL + a], 0.0);
     }
@@ -358,7 +358,7 @@ void ThermalCase::haloExchange(double* f)
 
 void ThermalCase::readReductions(int n)
 {
-    d2h(h_red, red.result, n, ctx->stream);
+    words_to_host(ctx, h_red, red.result, n * sizeof(double));
     ctx->sync();
 }
 
@@ -429,7 +429,7 @@ void ThermalCase::updateDimensions(heatSourceModel& hs)
     launch_isotherm_depth(ctx, dims, geo, cols, T, hs.spec.isoValue, pos, searchRadius, hs.staticDimensions[2], rankBelow >= 0,
                           rankAbove >= 0, red, R_DEPTH);
     ctx->allreduceMax(red.result + R_DEPTH, 1);
-    d2h(h_red + R_DEPTH, red.result + R_DEPTH, 1, ctx->stream);
+    words_to_host(ctx, h_red + R_DEPTH, red.result + R_DEPTH, sizeof(double));
     ctx->sync();
     hs.dimensions[0] = hs.staticDimensions[0]; hs.dimensions[1] = hs.staticDimensions[1]; hs.dimensions[2] = h_red[R_DEPTH];
 }
@@ -583,7 +583,7 @@ void ThermalCase::step(b200_step_report* rep)
     // solutionControls.H
     { ProfScope ps_(ctx, PC_QDOT); k_power<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, qDot, geo.V, red); B200_LAUNCH_CHECK(); }
     ctx->allreduceSum(red.result + R_POWER, 1);
-    d2h(h_red + R_POWER, red.result + R_POWER, 1, s);
+    words_to_host(ctx, h_red + R_POWER, red.result + R_POWER, sizeof(double));
     ctx->sync();
     const double totalPower = h_red[R_POWER];
     double nThermoCorr = ctl.nThermoCorrectors;
@@ -622,7 +622,7 @@ void ThermalCase::step(b200_step_report* rep)
         }
         evaluateT();                                                   // T.correctBoundaryConditions()
         ctx->allreduceMax(red.result + R_RESID, 1);
-        d2h(h_red + R_RESID, red.result + R_RESID, 1, s);
+        words_to_host(ctx, h_red + R_RESID, red.result + R_RESID, sizeof(double));
         ctx->sync();
         residual = h_red[R_RESID];
         nCorrDone = tCorr + 1;

@@ -7,7 +7,9 @@
   ([UPSTREAM] DICPreconditioner / DILUPreconditioner::calcReciprocalD + precondition, SURVEY.md Appendix A.7) and a PCG/DIC solve
   with the as-shipped controls (fvSolution:38-41) at the north-star tolerance -- this is the default schedule of the 100 M-cell
   benchmark (ticket order over thousands of tiles, ring reuse, sentinel re-arming at scale);
-* every selectable schedule (`B200_WAVE2_RING`, `B200_WAVE=1warp`, `B200_WAVE=multi`/`single`) on small and ragged blocks;
+* every selectable schedule -- `B200_WAVE=single` (k_wave2, one tile per CTA) with each ring geometry `B200_WAVE2_RING`,
+  `B200_WAVE=multi` (k_wave3, several tiles per CTA exchanging edges through shared memory) with each `B200_WAVE3` geometry,
+  `B200_WAVE=1warp` -- on small and ragged blocks (one tile, partial tiles, fewer tiles in J than a CTA holds, ...);
 * the full time step on the thin slab shape of the 8-GPU decomposition, 1000x400x8, five steps against the oracle at 1e-9.
 """
 import os
@@ -93,8 +95,10 @@ def test_many_tile_schedule_converging_solve(ctx, oracle):
     s.close()
 
 
-SCHEDULES = [dict(B200_WAVE2_RING="83"), dict(B200_WAVE2_RING="82"), dict(B200_WAVE2_RING="44"), dict(B200_WAVE2_RING="86"),
-             dict(B200_WAVE2_RING="84"), dict(B200_WAVE="1warp"), dict(B200_WAVE="single"), dict(B200_WAVE="multi")]
+SCHEDULES = [dict(B200_WAVE="single", B200_WAVE2_RING="83"), dict(B200_WAVE="single", B200_WAVE2_RING="82"),
+             dict(B200_WAVE="single", B200_WAVE2_RING="44"), dict(B200_WAVE="single", B200_WAVE2_RING="86"),
+             dict(B200_WAVE="single", B200_WAVE2_RING="84"), dict(B200_WAVE="1warp"), dict(B200_WAVE="multi"),
+             dict(B200_WAVE="multi", B200_WAVE3="444"), dict(B200_WAVE="multi", B200_WAVE3="248")]
 SMALL = [(150, 25, 15), (33, 17, 9), (7, 5, 3), (300, 7, 2), (40, 70, 9), (1, 4, 3), (64, 33, 5)]
 
 
@@ -118,7 +122,8 @@ def test_every_schedule_is_bit_exact_on_small_blocks(ctx, oracle, sched, precond
             assert np.array_equal(got, ref), (sched, dims)
 
 
-@pytest.mark.parametrize("sched", [dict(B200_WAVE2_RING="83"), dict(B200_WAVE="single"), dict(B200_WAVE="multi")],
+@pytest.mark.parametrize("sched", [dict(B200_WAVE="single", B200_WAVE2_RING="83"), dict(B200_WAVE="single"), dict(B200_WAVE="multi"),
+                                   dict(B200_WAVE="multi", B200_WAVE3="248")],
                          ids=lambda d: ",".join(f"{k[5:]}={v}" for k, v in d.items()))
 def test_schedules_at_three_million_cells(ctx, oracle, sched):
     """The schedules that run at scale, on a block with enough tiles to recycle ring slots and tickets many times over."""
