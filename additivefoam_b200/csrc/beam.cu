@@ -183,8 +183,8 @@ __global__ void __launch_bounds__(256) k_qdot_weights(BlockDims d, Geom g, Shape
     double acc = 0;
     for (int b = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); b < nBox; b += gridDim.x * warpsPerBlock) {
         const int i = box.i0 + b % bx, j = box.j0 + (b / bx) % by, k = box.k0 + b / (bx * by);
-        const double mnx = g.ox + i * g.dx, mxx = g.ox + (i + 1) * g.dx;
-        const double mny = g.oy + j * g.dy, mxy = g.oy + (j + 1) * g.dy;
+        const double mnx = g.ox + (i + g.i0) * g.dx, mxx = g.ox + (i + g.i0 + 1) * g.dx;
+        const double mny = g.oy + (j + g.j0) * g.dy, mxy = g.oy + (j + g.j0 + 1) * g.dy;
         const double mnz = g.oz + (k + g.k0) * g.dz, mxz = g.oz + (k + g.k0 + 1) * g.dz;
         double w = 0.0;
         // treeBoundBox::overlaps (inclusive)
@@ -295,8 +295,9 @@ BoxRange beam_box(const BlockDims& d, const Geom& g, const double pos[3], const 
     auto lo = [](double x, double o, double h, int n) { int v = (int)std::floor((x - o) / h) - 1; return std::min(std::max(v, 0), n); };
     auto hi = [](double x, double o, double h, int n) { int v = (int)std::floor((x - o) / h) + 2; return std::min(std::max(v, 0), n); };
     BoxRange b;
-    b.i0 = lo(pos[0] - 1.5 * dims[0], g.ox, g.dx, d.nx); b.i1 = hi(pos[0] + 1.5 * dims[0], g.ox, g.dx, d.nx);
-    b.j0 = lo(pos[1] - 1.5 * dims[1], g.oy, g.dy, d.ny); b.j1 = hi(pos[1] + 1.5 * dims[1], g.oy, g.dy, d.ny);
+    const double ox = g.ox + g.i0 * g.dx, oy = g.oy + g.j0 * g.dy;
+    b.i0 = lo(pos[0] - 1.5 * dims[0], ox, g.dx, d.nx); b.i1 = hi(pos[0] + 1.5 * dims[0], ox, g.dx, d.nx);
+    b.j0 = lo(pos[1] - 1.5 * dims[1], oy, g.dy, d.ny); b.j1 = hi(pos[1] + 1.5 * dims[1], oy, g.dy, d.ny);
     const double oz = g.oz + g.k0 * g.dz;
     b.k0 = lo(pos[2] - 1.5 * dims[2], oz, g.dz, d.nz); b.k1 = hi(pos[2] + 1.5 * dims[2], oz, g.dz, d.nz);
     return b;

@@ -274,6 +274,18 @@ int b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam* 
     B200_CATCH
 }
 
+int b200_beam_qdot_sub(b200_ctx* ctx, const b200_block_mesh* mesh, const int32_t offset[3], const int32_t nLocal[3], const b200_beam* beam,
+                       const double position[3], const double dimensions[3], double power, b200_reduce_sum_fn reduceSum, void* user,
+                       double* qDot, double* sumWeights, double* volumeUsed, double* absorbedPower)
+{
+    B200_TRY
+    B200_CHECK(ctx && mesh && offset && nLocal && beam && position && dimensions && qDot, "beam_qdot_sub: null argument");
+    B200_CUDA(cudaSetDevice(ctx->p->device));
+    const int off[3] = {offset[0], offset[1], offset[2]}, nl[3] = {nLocal[0], nLocal[1], nLocal[2]};
+    beam_qdot_standalone(ctx->p, *mesh, *beam, position, dimensions, power, qDot, sumWeights, volumeUsed, absorbedPower, off, nl, reduceSum, user);
+    B200_CATCH
+}
+
 static heatSourceModel host_model(const b200_beam* beam, const double dimensions[3])
 {
     B200_CHECK(beam != nullptr && dimensions != nullptr, "null beam or dimensions");

@@ -145,7 +145,7 @@ Ldu::~Ldu()
     for (auto& p : stage) dev_free(p);
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]); dev_free(waveOrderC[2]);
     dev_free(d_fStart); dev_free(d_fPos); dev_free(d_fFace); dev_free(d_bStart); dev_free(d_bPos); dev_free(d_bFace);
     dev_free(flowCoefF); dev_free(flowCoefB); dev_free(flowNumF); dev_free(flowRD); dev_free(flowF); dev_free(flowB);
     dev_free(flowPartial); dev_free(flowTicket);
@@ -174,7 +174,7 @@ void Ldu::setBlock(int nx, int ny, int nz)
     dev_free(rD);
     // the wave-order arrays, the tile order and the gathered coefficients belong to the block shape
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]); dev_free(waveOrderC[2]);
     waveEpoch = -1; waveUpper = nullptr; waveLower = nullptr;
 }
 
@@ -359,14 +359,15 @@ void Ldu::ensureWave(bool dilu)
         waveOrder = dev_alloc<int>(g.nTiles);
         B200_CUDA(cudaMemcpyAsync(waveOrder, order.data(), sizeof(int) * g.nTiles, cudaMemcpyHostToDevice, ctx->stream));
         // k_wave3: CTA tiles of NW tiles in J.  A J-hop between CTAs costs about NW tile lags, a K-hop one: hand out by 3*Jc + K
-        for (int q = 0; q < 2; q++) {
-            const int NW = q == 0 ? 4 : 2;
+        for (int q = 0; q < 3; q++) {
+            const int NW = q == 0 ? 4 : q == 1 ? 2 : 1;
             const int nJc = (g.nJ + NW - 1) / NW, nC = nJc * g.nK;
             std::vector<int> oc(nC);
             for (int t = 0; t < nC; t++) oc[t] = t;
-            static const int cJ = [] { const char* e = std::getenv("B200_WAVE3_ORDER_J"); return e ? std::atoi(e) : 3; }();
+            // relative start times of the CTA tiles: a J-hop costs about NW tile lags of WTJ-1 steps each, a K-hop WTK-1 steps
+            const long cJ = NW == 1 ? 9 : 3 * NW, cK = NW == 1 ? 7 : 4;
             std::stable_sort(oc.begin(), oc.end(), [&](int x, int y) {
-                return (long)cJ * (x % nJc) + (x / nJc) < (long)cJ * (y % nJc) + (y / nJc);
+                return cJ * (x % nJc) + cK * (x / nJc) < cJ * (y % nJc) + cK * (y / nJc);
             });
             waveOrderC[q] = dev_alloc<int>(nC);
             B200_CUDA(cudaMemcpyAsync(waveOrderC[q], oc.data(), sizeof(int) * nC, cudaMemcpyHostToDevice, ctx->stream));
@@ -444,9 +445,9 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         // geometry by B200_WAVE3 = <NW><GSZ><RNG> (tiles per CTA, steps per ring slot, ring slots); default 4 x 4 x 6
         const char* eg = std::getenv("B200_WAVE3");
         const int cfg = eg ? std::atoi(eg) : 446;
-        const int NWsel = cfg / 100 == 2 ? 2 : 4;
+        const int NWsel = cfg / 100 == 2 ? 2 : cfg / 100 == 1 ? 1 : 4;
         a.nCtas = ((a.g.nJ + NWsel - 1) / NWsel) * a.g.nK;
-        a.orderC = waveOrderC[NWsel == 4 ? 0 : 1];
+        a.orderC = waveOrderC[NWsel == 4 ? 0 : NWsel == 2 ? 1 : 2];
         auto launch3 = [&](auto kernel, size_t shm, int threads) {
             static std::set<const void*> configured;
             if (configured.insert((const void*)kernel).second)
@@ -471,6 +472,8 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         } while (0)
         if (cfg == 444) B200_W3(4, 4, 4, 4);
         else if (cfg == 248) B200_W3(4, 8, 8, 2);
+        else if (cfg == 183) B200_W3(8, 3, 3, 1);
+        else if (cfg == 146) B200_W3(4, 6, 6, 1);
         else B200_W3(4, 6, 5, 4);
 #undef B200_W3
     } else {

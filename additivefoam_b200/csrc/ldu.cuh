@@ -112,7 +112,7 @@ public:
     double* wave[14] = {nullptr};    // A0 PX PY PZ QX QY QZ WF RF WB NX NY NZ DG
     int* waveFlags = nullptr;        // tile ticket
     int* waveOrder = nullptr;        // ticket -> tile
-    int* waveOrderC[2] = {nullptr, nullptr};   // ticket -> CTA tile of k_wave3 (4 / 2 tiles per CTA)
+    int* waveOrderC[3] = {nullptr, nullptr, nullptr};   // ticket -> CTA tile of k_wave3 (4 / 2 / 1 tiles per CTA)
     long long* waveTrace = nullptr;  // B200_WAVE_TRACE diagnostic
     double* wavePartial = nullptr;
     int64_t waveLen = 0;

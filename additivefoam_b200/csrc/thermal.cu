@@ -637,15 +637,21 @@ void ThermalCase::step(b200_step_report* rep)
     if (solidOn) solidificationExecute();                              // [UPSTREAM] Time::run -> functionObjectList::execute
 }
 
-// heatSourceModel::qDot() on its own (B2 of the drop-in boundary)
+// heatSourceModel::qDot() on its own (B2 of the drop-in boundary).  `offset` / `nLocal`: this process owns the sub-block of
+// nLocal cells starting at global index `offset` of the blockMesh block `bm` (one rank of a decomposed run; points are those
+// of the global block, min + (i0 + i)*d).  `reduceSum`: how the ranks add up sum(V*w) before the 5 % rule
+// (fvc::domainIntegrate, heatSourceModel.C:359) -- the OpenFOAM-side shim passes its own Pstream reduce.
 void beam_qdot_standalone(Ctx* ctx, const b200_block_mesh& bm, const b200_beam& beam, const double position[3], const double dimensions[3],
-                          double power, double* qDotOut, double* sumWeights, double* volumeUsed, double* absorbedPowerOut)
+                          double power, double* qDotOut, double* sumWeights, double* volumeUsed, double* absorbedPowerOut,
+                          const int* offset, const int* nLocal, double (*reduceSum)(double, void*), void* user)
 {
-    BlockDims d; d.nx = bm.nx; d.ny = bm.ny; d.nz = bm.nz;
+    BlockDims d; d.nx = nLocal ? nLocal[0] : bm.nx; d.ny = nLocal ? nLocal[1] : bm.ny; d.nz = nLocal ? nLocal[2] : bm.nz;
     Geom g{};
     g.ox = bm.min[0]; g.oy = bm.min[1]; g.oz = bm.min[2];
     g.dx = (bm.max[0] - bm.min[0]) / bm.nx; g.dy = (bm.max[1] - bm.min[1]) / bm.ny; g.dz = (bm.max[2] - bm.min[2]) / bm.nz;
-    g.V = g.dx * g.dy * g.dz; g.k0 = 0;
+    g.V = g.dx * g.dy * g.dz; g.k0 = offset ? offset[2] : 0; g.i0 = offset ? offset[0] : 0; g.j0 = offset ? offset[1] : 0;
+    B200_CHECK(d.nx > 0 && d.ny > 0 && d.nz > 0 && g.i0 >= 0 && g.j0 >= 0 && g.k0 >= 0 && g.i0 + d.nx <= bm.nx && g.j0 + d.ny <= bm.ny
+               && g.k0 + d.nz <= bm.nz, "sub-block outside the block");
     const size_t n = (size_t)d.nCells();
     b200_beam spec = beam; spec.nSegments = 0; spec.path = nullptr;
     heatSourceModel hs(spec, 0.0, 0.0);
@@ -671,6 +677,14 @@ void beam_qdot_standalone(Ctx* ctx, const b200_block_mesh& bm, const b200_beam& 
         const size_t nb = (size_t)std::max(box.i1 - box.i0, 0) * std::max(box.j1 - box.j0, 0) * std::max(box.k1 - box.k0, 0);
         wb = dev_alloc<double>(nb + 1);
         launch_qdot_weights(ctx, d, g, sp, box, wb, red, R_SUMW);
+        if (reduceSum) {          // every rank calls in, also those the beam does not touch (a collective, like gSum)
+            double local = 0;
+            d2h(&local, red.result + R_SUMW, 1, ctx->stream);
+            ctx->sync();
+            const double global = reduceSum(local, user);
+            h2d(red.result + R_SUMW, &global, 1, ctx->stream);
+            ctx->sync();
+        }
         launch_qdot_apply(ctx, d, box, wb, q, absorbed, V0, red.result + R_SUMW, 0.0, 0.0, 2, red.result + R_VOLUME);
         double h[R_NSLOTS];
         d2h(h, red.result, R_NSLOTS, ctx->stream);

@@ -30,6 +30,7 @@ struct Geom {
     double dcx, dcy, dcz;       // deltaCoeffs of internal faces
     double bcx, bcy, bcz;       // deltaCoeffs of boundary faces (cell centre to face)
     int k0;                     // global k index of local plane 0
+    int i0 = 0, j0 = 0;         // global i, j index of local cell (0, 0, .): a sub-block of the blockMesh block (b200_beam_qdot_sub)
 };
 
 constexpr int SIDE_PROCESSOR = 3;     // extends B200_BC_*
@@ -139,12 +140,13 @@ private:
     void assembleBase(bool explicitSolve, double rDeltaT);
     void readReductions(int n);
     friend void beam_qdot_standalone(Ctx*, const b200_block_mesh&, const b200_beam&, const double*, const double*, double, double*,
-                                     double*, double*, double*);
+                                     double*, double*, double*, const int*, const int*, double (*)(double, void*), void*);
 };
 
 void beam_qdot_standalone(Ctx* ctx, const b200_block_mesh& mesh, const b200_beam& beam, const double position[3],
                           const double dimensions[3], double power, double* qDot, double* sumWeights, double* volumeUsed,
-                          double* absorbedPower);
+                          double* absorbedPower, const int* offset = nullptr, const int* nLocal = nullptr,
+                          double (*reduceSum)(double, void*) = nullptr, void* user = nullptr);
 
 // device entry points of beam.cu
 void launch_qdot_weights(Ctx* ctx, const BlockDims& d, const Geom& g, const ShapeParams& sp, const BoxRange& box, double* wbuf,

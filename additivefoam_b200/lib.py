@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.environ.get("B200_LIBRARY") or os.path.join(_HERE, "libadditivefoam_b200.so")
 
 dp, ip = abi.c_double_p, abi.c_int32_p
+REDUCE_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)      # b200_reduce_sum_fn
 
 #: every symbol include/additivefoam_b200.h declares
 SYMBOLS = [
@@ -27,7 +28,7 @@ SYMBOLS = [
     "b200_ctx_peer_export", "b200_ctx_peer_export_halo", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
-    "b200_beam_qdot", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_mixed_temperature_value_fraction", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
+    "b200_beam_qdot", "b200_beam_qdot_sub", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_mixed_temperature_value_fraction", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
     "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_set_field_async", "b200_case_apply_staged",
     "b200_case_get_field_async", "b200_case_transfers_wait", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_sources_update", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
@@ -97,6 +98,7 @@ def load():
     L.b200_ldu_precondition.argtypes = [vp, C.c_int32, dp, dp, dp, dp, dp]
     L.b200_ldu_levels.argtypes = [vp, ip, ip]
     L.b200_beam_qdot.argtypes = [vp, C.POINTER(abi.BlockMesh), C.POINTER(abi.Beam), dp, dp, C.c_double, dp, dp, dp, dp]
+    L.b200_beam_qdot_sub.argtypes = [vp, C.POINTER(abi.BlockMesh), ip, ip, C.POINTER(abi.Beam), dp, dp, C.c_double, REDUCE_FN, vp, dp, dp, dp, dp]
     L.b200_beam_shape_v0.argtypes = [C.POINTER(abi.Beam), dp, dp, dp]
     L.b200_beam_shape_weight.argtypes = [C.POINTER(abi.Beam), dp, dp, dp]
     L.b200_beam_absorption_eta.argtypes = [C.POINTER(abi.Beam), C.c_double, dp]
@@ -300,6 +302,26 @@ def beam_qdot(ctx, mesh, beam, position, dimensions, power):
     sw, vol, ap = C.c_double(), C.c_double(), C.c_double()
     _check(L.b200_beam_qdot(ctx.h, C.byref(bm), C.byref(b), _P(pos), _P(dims), power, _P(out),
                             C.cast(C.byref(sw), dp), C.cast(C.byref(vol), dp), C.cast(C.byref(ap), dp)))
+    return out, sw.value, vol.value, ap.value
+
+
+def beam_qdot_sub(ctx, mesh, offset, n_local, beam, position, dimensions, power, reduce_sum):
+    """heatSourceModel::qDot() of one rank's sub-block (b200_beam_qdot_sub): `reduce_sum(local) -> global` plays the part of
+    the reference's parallel reduction of sum(V*w).  Returns (qDot[local cells], sumWeights, volumeUsed, absorbedPower)."""
+    L = ctx.L
+    bm = abi.BlockMesh()
+    bm.nx, bm.ny, bm.nz = mesh["n"]
+    for q in range(3):
+        bm.min[q], bm.max[q] = mesh["min"][q], mesh["max"][q]
+    b = cases.make_beam(beam)
+    off = np.ascontiguousarray(offset, dtype=np.int32)
+    nl = np.ascontiguousarray(n_local, dtype=np.int32)
+    out = np.empty(int(nl[0]) * int(nl[1]) * int(nl[2]))
+    pos, dims = _f64(position), _f64(dimensions)
+    sw, vol, ap = C.c_double(), C.c_double(), C.c_double()
+    cb = REDUCE_FN(lambda v, user: float(reduce_sum(v)))
+    _check(L.b200_beam_qdot_sub(ctx.h, C.byref(bm), off.ctypes.data_as(ip), nl.ctypes.data_as(ip), C.byref(b), _P(pos), _P(dims), power,
+                                cb, None, _P(out), C.cast(C.byref(sw), dp), C.cast(C.byref(vol), dp), C.cast(C.byref(ap), dp)))
     return out, sw.value, vol.value, ap.value
 
 

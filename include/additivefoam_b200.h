@@ -241,6 +241,16 @@ int  b200_ldu_levels(b200_ldu* ldu, int32_t* levelOfCell, int32_t* nLevels);
 int  b200_beam_qdot(b200_ctx* ctx, const b200_block_mesh* mesh, const b200_beam* beam,
                     const double position[3], const double dimensions[3], double power,
                     double* qDot, double* sumWeights, double* volumeUsed, double* absorbedPower);
+/* The same for ONE RANK of a decomposed run (heatSourceModel.C:287-353 loops over the rank's own cells; the normalisation
+ * sum of :359 is global): the rank owns the sub-block of nLocal[] cells that starts at global cell index offset[] of `mesh`
+ * (a `simple` / `hierarchical` decomposition of a blockMesh block; cell corners are those of the global block).  `reduceSum` adds
+ * the ranks' local sum(V*w) -- the shim passes a function that calls Foam::reduce(..., sumOp<scalar>()); every rank must call in,
+ * also those the beam does not touch.  qDot: nLocal[0]*nLocal[1]*nLocal[2] values in the rank's local cell order. */
+typedef double (*b200_reduce_sum_fn)(double localValue, void* user);
+int  b200_beam_qdot_sub(b200_ctx* ctx, const b200_block_mesh* mesh, const int32_t offset[3], const int32_t nLocal[3],
+                        const b200_beam* beam, const double position[3], const double dimensions[3], double power,
+                        b200_reduce_sum_fn reduceSum, void* user, double* qDot, double* sumWeights, double* volumeUsed,
+                        double* absorbedPower);
 
 /* The two pure virtuals of heatSourceModel (heatSourceModel.H:197-200) and absorptionModel::eta, evaluated by the library's host
  * mirror of the beam models (no device, no context): V0() for the given current dimensions -- for projectedGaussian it also

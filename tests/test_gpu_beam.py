@@ -67,3 +67,36 @@ def test_power_conservation(ctx):
     assert ap == pytest.approx(0.33 * 179.2)
     if abs(1 - sw / vol) < 1e-12:          # normalised with the numerical volume
         assert got.sum() * V == pytest.approx(ap, rel=1e-12)
+
+
+@pytest.mark.parametrize("name", ["superGaussian", "modifiedSuperGaussian_deep", "projectedGaussian"])
+@pytest.mark.parametrize("split", [(2, 1, 1), (1, 3, 1), (1, 1, 2), (2, 3, 2)])
+def test_qdot_of_a_decomposed_block_equals_the_serial_field(ctx, name, split):
+    """b200_beam_qdot_sub, the per-rank form the OpenFOAM-side shim calls in a parallel run (heatSourceModel.C:287-353 loops over
+    the rank's own cells, :359 sums V*w over all ranks): every sub-block of a `simple (nx ny nz)` decomposition of the block is
+    evaluated on its own with the global sum handed in through the reduce callback; stitched together the pieces are the serial
+    field bit for bit (same cell corners, same sample points, same normalisation), wherever the beam sits relative to the cuts."""
+    beam, dims = BEAMS[name]
+    n = MESH["n"]
+    for pos in [(1.234e-4, 1.7e-5, 0.0), (0.0002, 0.0, 0.0), (0.0003, 0.0, -0.00012)]:
+        ref, rsw, rvol, rap = lib.beam_qdot(ctx, MESH, beam, pos, dims, 150.0)
+        cuts = [[n[a] * r // split[a] for r in range(split[a] + 1)] for a in range(3)]
+        blocks = [((cuts[0][a], cuts[1][b], cuts[2][c]), (cuts[0][a + 1] - cuts[0][a], cuts[1][b + 1] - cuts[1][b], cuts[2][c + 1] - cuts[2][c]))
+                  for c in range(split[2]) for b in range(split[1]) for a in range(split[0])]
+        # pass 1: every rank's local sum (the callback sees it); pass 2: the same call with the global sum returned
+        local = []
+        for off, nl in blocks:
+            lib.beam_qdot_sub(ctx, MESH, off, nl, beam, pos, dims, 150.0, lambda v: (local.append(v), v)[1])
+        total = 0.0
+        for v in local:            # rank order, as [UPSTREAM] gSum adds the partial sums
+            total += v
+        full = np.zeros(n[0] * n[1] * n[2]).reshape(n[2], n[1], n[0])
+        for off, nl in blocks:
+            q, sw, vol, ap = lib.beam_qdot_sub(ctx, MESH, off, nl, beam, pos, dims, 150.0, lambda v: total)
+            full[off[2]:off[2] + nl[2], off[1]:off[1] + nl[1], off[0]:off[0] + nl[0]] = q.reshape(nl[2], nl[1], nl[0])
+            assert ap == rap
+        full = full.ravel()
+        assert np.array_equal(full == 0.0, ref == 0.0)
+        # the sum of the pieces' sums differs from the serial grid-wide sum by rounding only; with it the fields agree to that rounding
+        assert total == pytest.approx(rsw, rel=1e-13)
+        assert np.max(np.abs(full - ref)) <= 1e-13 * np.abs(ref).max()

@@ -98,7 +98,8 @@ def test_many_tile_schedule_converging_solve(ctx, oracle):
 SCHEDULES = [dict(B200_WAVE="single", B200_WAVE2_RING="83"), dict(B200_WAVE="single", B200_WAVE2_RING="82"),
              dict(B200_WAVE="single", B200_WAVE2_RING="44"), dict(B200_WAVE="single", B200_WAVE2_RING="86"),
              dict(B200_WAVE="single", B200_WAVE2_RING="84"), dict(B200_WAVE="1warp"), dict(B200_WAVE="multi"),
-             dict(B200_WAVE="multi", B200_WAVE3="444"), dict(B200_WAVE="multi", B200_WAVE3="248")]
+             dict(B200_WAVE="multi", B200_WAVE3="444"), dict(B200_WAVE="multi", B200_WAVE3="248"), dict(B200_WAVE="multi", B200_WAVE3="183"),
+             dict(B200_WAVE="multi", B200_WAVE3="146")]
 SMALL = [(150, 25, 15), (33, 17, 9), (7, 5, 3), (300, 7, 2), (40, 70, 9), (1, 4, 3), (64, 33, 5)]
 
 
