@@ -1,5 +1,6 @@
 #include "ldu_kernels.cuh"
 #include "wave_kernels.cuh"
+#include "wave4_kernels.cuh"
 #include "flow_kernels.cuh"
 #include <cstdlib>
 #include <set>
@@ -405,7 +406,7 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     a.trace = nullptr; a.nCtas = 0; a.orderC = nullptr;
     static const bool traceOn = [] { const char* e = std::getenv("B200_WAVE_TRACE"); return e && std::atoi(e) != 0; }();
     if (traceOn) {
-        if (!waveTrace) waveTrace = dev_alloc<long long>((size_t)a.g.nTiles * 12);
+        if (!waveTrace) { waveTrace = dev_alloc<long long>((size_t)a.g.nTiles * WTRACE); B200_CUDA(cudaMemsetAsync(waveTrace, 0, (size_t)a.g.nTiles * WTRACE * sizeof(long long), ctx->stream)); }
         a.trace = waveTrace;
     }
     {
@@ -429,8 +430,9 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     // B200_WAVE: "1warp" the one-warp kernel, "single" k_wave2 (one tile per CTA), "multi" k_wave3 (NW tiles per CTA); default:
     // k_wave3 where the dependency chain across tiles bounds the sweep (few tiles: thin slabs, small blocks), k_wave2 where
     // bandwidth does (thousands of tiles)
-    const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : std::string(e) == "multi" ? 3 : 2; }();
+    const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : std::string(e) == "multi" ? 3 : std::string(e) == "tri" ? 4 : 2; }();
     const bool oneWarp = forced == 1;
+    const bool tri = forced == 4;
     const bool multi = forced == 3 || (forced == 0 && a.g.nTiles <= 1536);
     if (op == 0 && !oneWarp) {      // the warp-specialised factor sweep streams the diagonal from wave order as well
         k_wave_from_natural<<<waveVecGrid(), 256, 0, s>>>(a.g, rA, wave[13], 1.0, d_state); B200_LAUNCH_CHECK();
@@ -441,6 +443,38 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         else if (wio) { if (dot) k_wave<2, false, true, true><<<grid, 32, 0, s>>>(a); else k_wave<2, false, false, true><<<grid, 32, 0, s>>>(a); }
         else if (dot) k_wave<2, false, true, false><<<grid, 32, 0, s>>>(a);
         else k_wave<2, false, false, false><<<grid, 32, 0, s>>>(a);
+    } else if (tri) {
+        // k_wave4 (wave4_kernels.cuh): compute / halo / stream warps per tile; ring geometry as for k_wave2
+        auto launch4 = [&](auto kernel, size_t shm) {
+            static std::set<const void*> configured;
+            if (configured.insert((const void*)kernel).second)
+                B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shm));
+            kernel<<<grid, 96, shm, s>>>(a);
+        };
+        const char* eg = std::getenv("B200_WAVE2_RING");
+        const int cfg = eg ? std::atoi(eg) : (a.g.nTiles > 1536 ? 83 : 86);
+#define B200_W4(G_, R_)                                                                                                                        \
+        do {                                                                                                                                   \
+            if (op == 0) { if (dilu) launch4(k_wave4<0, true, false, true, true, G_, R_>, sizeof(WaveSmem<0, true, true, G_, R_>));                     \
+                           else launch4(k_wave4<0, false, false, true, true, G_, R_>, sizeof(WaveSmem<0, false, true, G_, R_>)); }                      \
+            else if (op == 1) { if (wio) launch4(k_wave4<1, false, false, true, false, G_, R_>, sizeof(WaveSmem<1, false, true, G_, R_>));               \
+                                else launch4(k_wave4<1, false, false, false, false, G_, R_>, sizeof(WaveSmem<1, false, false, G_, R_>)); }               \
+            else if (wio) { if (dot) launch4(k_wave4<2, false, true, true, false, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>));                    \
+                            else launch4(k_wave4<2, false, false, true, false, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>)); }                     \
+            else if (dot) launch4(k_wave4<2, false, true, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                             \
+            else launch4(k_wave4<2, false, false, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                                     \
+            if (op == 0) {                                                                                                                     \
+                k_wave_refactor_prepare<<<ctx->smCount * 4, 256, 0, s>>>(a, waveLen);                                                          \
+                if (dilu) launch4(k_wave4<0, true, false, true, false, G_, R_>, sizeof(WaveSmem<0, true, true, G_, R_>));                                \
+                else launch4(k_wave4<0, false, false, true, false, G_, R_>, sizeof(WaveSmem<0, false, true, G_, R_>));                                   \
+            }                                                                                                                                  \
+        } while (0)
+        if (cfg == 83) B200_W4(8, 3);
+        else if (cfg == 84) B200_W4(8, 4);
+        else if (cfg == 48) B200_W4(4, 8);
+        else if (cfg == 412) B200_W4(4, 12);
+        else B200_W4(8, 6);
+#undef B200_W4
     } else if (multi) {
         // geometry by B200_WAVE3 = <NW><GSZ><RNG> (tiles per CTA, steps per ring slot, ring slots); default 4 x 4 x 6
         const char* eg = std::getenv("B200_WAVE3");
@@ -502,6 +536,8 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         else if (cfg == 83) B200_W2(8, 3);
         else if (cfg == 82) B200_W2(8, 2);
         else if (cfg == 86) B200_W2(8, 6);
+        else if (cfg == 412) B200_W2(4, 12);
+        else if (cfg == 48) B200_W2(4, 8);
         else B200_W2(8, 4);
 #undef B200_W2
         if (op == 0) {
@@ -514,15 +550,16 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     }
     B200_LAUNCH_CHECK();
     if (traceOn) {          // diagnostic: per-tile time stamps of this sweep, relative to the earliest, on stderr
-        std::vector<long long> h((size_t)a.g.nTiles * 12);
+        std::vector<long long> h((size_t)a.g.nTiles * WTRACE);
         d2h(h.data(), waveTrace, h.size(), s);
         ctx->sync();
         long long t0 = h[11];
-        for (int t = 0; t < a.g.nTiles; t++) t0 = std::min(t0, h[12 * t + 11]);
+        for (int t = 0; t < a.g.nTiles; t++) t0 = std::min(t0, h[WTRACE * t + 11]);
         std::fprintf(stderr, "WAVE_TRACE op %d nJ %d nK %d\n", op, a.g.nJ, a.g.nK);
         for (int t = 0; t < a.g.nTiles; t++) {
             std::fprintf(stderr, "WT %d %d", t % a.g.nJ, t / a.g.nJ);
-            for (int q = 0; q < 12; q++) std::fprintf(stderr, " %lld", h[12 * t + q] - t0);
+            for (int q = 0; q < 12; q++) std::fprintf(stderr, " %lld", h[WTRACE * t + q] - t0);
+            for (int q = 12; q < WTRACE; q++) std::fprintf(stderr, " %lld", h[WTRACE * t + q]);
             std::fprintf(stderr, "\n");
         }
     }

@@ -97,7 +97,10 @@ def test_many_tile_schedule_converging_solve(ctx, oracle):
 
 SCHEDULES = [dict(B200_WAVE="single", B200_WAVE2_RING="83"), dict(B200_WAVE="single", B200_WAVE2_RING="82"),
              dict(B200_WAVE="single", B200_WAVE2_RING="44"), dict(B200_WAVE="single", B200_WAVE2_RING="86"),
-             dict(B200_WAVE="single", B200_WAVE2_RING="84"), dict(B200_WAVE="1warp"), dict(B200_WAVE="multi"),
+             dict(B200_WAVE="single", B200_WAVE2_RING="84"), dict(B200_WAVE="single", B200_WAVE2_RING="412"),
+             dict(B200_WAVE="single", B200_WAVE2_RING="48"), dict(B200_WAVE="tri", B200_WAVE2_RING="86"), dict(B200_WAVE="tri", B200_WAVE2_RING="83"),
+             dict(B200_WAVE="tri", B200_WAVE2_RING="84"), dict(B200_WAVE="tri", B200_WAVE2_RING="48"), dict(B200_WAVE="tri", B200_WAVE2_RING="412"),
+             dict(B200_WAVE="1warp"), dict(B200_WAVE="multi"),
              dict(B200_WAVE="multi", B200_WAVE3="444"), dict(B200_WAVE="multi", B200_WAVE3="248"), dict(B200_WAVE="multi", B200_WAVE3="183"),
              dict(B200_WAVE="multi", B200_WAVE3="146")]
 SMALL = [(150, 25, 15), (33, 17, 9), (7, 5, 3), (300, 7, 2), (40, 70, 9), (1, 4, 3), (64, 33, 5)]
@@ -124,6 +127,7 @@ def test_every_schedule_is_bit_exact_on_small_blocks(ctx, oracle, sched, precond
 
 
 @pytest.mark.parametrize("sched", [dict(B200_WAVE="single", B200_WAVE2_RING="83"), dict(B200_WAVE="single"), dict(B200_WAVE="multi"),
+                                   dict(B200_WAVE="tri", B200_WAVE2_RING="83"), dict(B200_WAVE="tri", B200_WAVE2_RING="86"),
                                    dict(B200_WAVE="multi", B200_WAVE3="248")],
                          ids=lambda d: ",".join(f"{k[5:]}={v}" for k, v in d.items()))
 def test_schedules_at_three_million_cells(ctx, oracle, sched):
