@@ -620,7 +620,9 @@ void ThermalCase::step(b200_step_report* rep)
             iterSum += perf.nIterations;
             { ProfScope ps_(ctx, PC_ALPHA); k_alpha_update<<<flat_grid(ctx, (int64_t)n), BLK, 0, s>>>((int64_t)n, T, dFdT, T0, alpha1, red); B200_LAUNCH_CHECK(); }
         }
-        evaluateT();                                                   // T.correctBoundaryConditions()
+        evaluateT();                                                   // psi.correctBoundaryConditions() at the end of solveSegregated
+        evaluateT();                                                   // TEqn.H:44 T.correctBoundaryConditions(): the patches are not "updated" any more, so
+                                                                       // mixedTemperature recomputes its value fraction from the new face values first
         ctx->allreduceMax(red.result + R_RESID, 1);
         words_to_host(ctx, h_red + R_RESID, red.result + R_RESID, sizeof(double));
         ctx->sync();

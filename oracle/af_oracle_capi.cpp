@@ -307,6 +307,17 @@ int afo_case_pre_step_state(void* h, scalar* Told)
     std::copy(c->rk[0].Told.begin(), c->rk[0].Told.end(), Told);
     return 0;
 }
+// Test probes: the patch fields of T (single-rank cases): number of physical patches, faces of patch p, its face values and value
+// fractions in the oracle's face order (block sides in blockMesh order).
+int afo_case_n_patches(void* h) { Case* c = (Case*)h; return c->R == 1 ? (int)c->rk[0].mesh.patches.size() : -1; }
+int64_t afo_case_patch_size(void* h, int p) { return (int64_t)((Case*)h)->rk[0].mesh.patches[p].faceCells.size(); }
+int afo_case_patch_state(void* h, int p, scalar* Tb, scalar* valueFraction)
+{
+    const Patch& pa = ((Case*)h)->rk[0].mesh.patches[p];
+    if (Tb) std::copy(pa.Tb.begin(), pa.Tb.end(), Tb);
+    if (valueFraction) std::copy(pa.valueFraction.begin(), pa.valueFraction.end(), valueFraction);
+    return 0;
+}
 scalar afo_mixed_value_fraction(scalar h, scalar emissivity, scalar Tinf, scalar Tp, scalar kap, scalar deltaCoeff)
 {
     return mixedValueFraction(h, emissivity, Tinf, Tp, kap, deltaCoeff);

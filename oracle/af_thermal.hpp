@@ -903,6 +903,11 @@ inline void Case::step(b200_step_report* rep)
         forRanks(R, [&](int r) { thermoSource(r); });
         perf = solveCorrector(explicitSolve, rDeltaT, rDeltaT);
         iterSum += perf.nIterations;
+        // TEqn.H:44 T.correctBoundaryConditions() -- a SECOND evaluate after the one at the end of solveSegregated: the patches are
+        // no longer "updated", so mixedTemperature recomputes its value fraction from the face temperatures the first evaluate
+        // left and evaluates again.  (Found by including TEqn.H verbatim, oracle/_ref/refTEqn: without this the internal field of
+        // the step is the same, but the face values and value fractions that enter the NEXT step's matrix are not.)
+        forRanks(R, [&](int r) { correctTBoundary(r); });
         std::vector<scalar> pr(R, 0.0);
         forRanks(R, [&](int r) {
             RankState& s = rk[r];

@@ -41,6 +41,10 @@ def load():
     L.afo_case_isotherm_depth.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.afo_case_sources_probe.argtypes = [C.c_void_p, C.c_double, dp]
     L.afo_case_pre_step_state.argtypes = [C.c_void_p, dp]
+    L.afo_case_n_patches.argtypes = [C.c_void_p]
+    L.afo_case_patch_size.restype = C.c_int64
+    L.afo_case_patch_size.argtypes = [C.c_void_p, C.c_int]
+    L.afo_case_patch_state.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.afo_mixed_value_fraction.restype = C.c_double
     L.afo_mixed_value_fraction.argtypes = [C.c_double] * 6
     for f in ("afo_case_time", "afo_case_Tliq", "afo_case_Tsol"):
@@ -109,6 +113,16 @@ class OracleCase:
         Told = np.empty(self.n, dtype=np.float64)
         assert self.L.afo_case_pre_step_state(self.h, P(Told)) == 0
         return Told
+
+    def patch_state(self):
+        """[(Tb, valueFraction)] of the physical patches of T, in the oracle's face order (single-rank cases)."""
+        out = []
+        for p in range(self.L.afo_case_n_patches(self.h)):
+            n = self.L.afo_case_patch_size(self.h, p)
+            Tb, vf = np.empty(n), np.empty(n)
+            self.L.afo_case_patch_state(self.h, p, P(Tb), P(vf))
+            out.append((Tb, vf))
+        return out
 
     def sources_probe(self, proposed_dt):
         """adjustDeltaT + update of the sources over [time, time + dt], time += dt; returns the adjusted dt (qDot: field(FIELD_QDOT))."""
