@@ -38,6 +38,14 @@ int b200_nccl_unique_id(void* out128)
     B200_CATCH
 }
 
+int b200_device_count(int* count)
+{
+    B200_TRY
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) throw Error("no CUDA device available: the B200 path has no CPU fallback");
+    *count = n;
+    B200_CATCH
+}
 int b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, int nranks, b200_ctx** out)
 {
     B200_TRY

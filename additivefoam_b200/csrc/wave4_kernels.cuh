@@ -26,39 +26,47 @@ namespace b200 {
 
 // operands of HS consecutive steps of one lane, in registers
 template <int OP, bool DILU, bool FASTDIV, int HS> struct WaveOps {
-    double c0[HS], c1[HS], c2[HS], c3[HS], in[HS], hy[HS], hz[HS];
+    double c0[HS], c1[HS], c2[HS], c3[HS], in[HS];
     double n1[(OP == 0 && DILU) ? HS : 1], n2[(OP == 0 && DILU) ? HS : 1], n3[(OP == 0 && DILU) ? HS : 1];
-    double yY[(OP == 0 && FASTDIV) ? HS : 1], yZ[(OP == 0 && FASTDIV) ? HS : 1];      // refined reciprocals of the halo diagonals
 };
 
 // ring slot -> registers, with everything that does not depend on the chain formed on the way ((rD*coef) exactly as the
 // reference's loops round it; rD*rA)
 template <int OP, bool DILU, bool WIO, bool FASTDIV, int NARR, int HS, class Slot>
+__device__ __forceinline__ void wave4_fetch_one(const Slot& S, int s0, int lane, WaveOps<OP, DILU, FASTDIV, HS>& r, int s)
+{
+    const int o = (s0 + s) * 32 + lane;
+    if (OP == 0) {
+        r.c0[s] = WIO ? S.arr[NARR - 1][o] : S.in[o]; r.c1[s] = S.arr[0][o]; r.c2[s] = S.arr[1][o]; r.c3[s] = S.arr[2][o]; r.in[s] = 0.0;
+        if (DILU) { r.n1[s] = S.arr[3][o]; r.n2[s] = S.arr[4][o]; r.n3[s] = S.arr[5][o]; }
+    } else {
+        const double rd = OP == 1 ? S.arr[0][o] : S.arr[5][o];
+        r.in[s] = (OP == 1 && !WIO) ? S.in[o] : S.arr[4][o];
+        r.c0[s] = OP == 1 ? rd * r.in[s] : S.arr[0][o];
+        r.c1[s] = rd * S.arr[1][o]; r.c2[s] = rd * S.arr[2][o]; r.c3[s] = rd * S.arr[3][o];
+    }
+}
+template <int OP, bool DILU, bool WIO, bool FASTDIV, int NARR, int HS, class Slot>
 __device__ __forceinline__ void wave4_fetch(const Slot& S, int s0, int lane, WaveOps<OP, DILU, FASTDIV, HS>& r)
 {
 #pragma unroll
-    for (int s = 0; s < HS; s++) {
-        const int o = (s0 + s) * 32 + lane;
-        r.hy[s] = S.hy[o]; r.hz[s] = S.hz[o];
-        if (OP == 0) {
-            r.c0[s] = WIO ? S.arr[NARR - 1][o] : S.in[o]; r.c1[s] = S.arr[0][o]; r.c2[s] = S.arr[1][o]; r.c3[s] = S.arr[2][o]; r.in[s] = 0.0;
-            if (DILU) { r.n1[s] = S.arr[3][o]; r.n2[s] = S.arr[4][o]; r.n3[s] = S.arr[5][o]; }
-            if (FASTDIV) { r.yY[s] = div_refine(r.hy[s]); r.yZ[s] = div_refine(r.hz[s]); }
-        } else {
-            const double rd = OP == 1 ? S.arr[0][o] : S.arr[5][o];
-            r.in[s] = (OP == 1 && !WIO) ? S.in[o] : S.arr[4][o];
-            r.c0[s] = OP == 1 ? rd * r.in[s] : S.arr[0][o];
-            r.c1[s] = rd * S.arr[1][o]; r.c2[s] = rd * S.arr[2][o]; r.c3[s] = rd * S.arr[3][o];
-        }
-    }
+    for (int s = 0; s < HS; s++) wave4_fetch_one<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(S, s0, lane, r, s);
 }
 
 // HS steps of the recurrence (t0 = lowest step of the half; the backward sweep walks it downwards).  The arithmetic of a step is
 // that of wave2_compute, operation for operation.
-template <int OP, bool DILU, bool DOT, bool RAMP, bool WIO, bool FASTDIV, int HS>
-__device__ __forceinline__ void wave4_chain(const WaveOps<OP, DILU, FASTDIV, HS>& r, const WaveOut<OP>& out, int t0, int lane, int skew, int nx,
-                                            bool pencil, bool edgeInY, bool edgeInZ, bool hasY, bool hasZ, double& last, double& acc, double& held,
-                                            unsigned& bad)
+// PRE: the operands of the NEXT half (slot Sn, first step sn0) are fetched into `nxt` step by step between the steps of this chain --
+// written interleaved in the source because the compiler keeps a separate fetch loop in front of the chain (the divergence check
+// of the first shuffle ends its scheduling window), where the warp then waits out the LDS latency and 16 DMULs before every half.
+// halo operands of HS steps (the neighbour tiles' results on this tile's upstream edges; for the factor sweep with their refined reciprocals)
+template <int OP, bool FASTDIV, int HS> struct WaveHalo {
+    double hy[HS], hz[HS];
+    double yY[(OP == 0 && FASTDIV) ? HS : 1], yZ[(OP == 0 && FASTDIV) ? HS : 1];
+};
+template <int OP, bool DILU, bool DOT, bool RAMP, bool WIO, bool FASTDIV, int HS, bool PRE = false, int NARR = 1, class Slot = int>
+__device__ __forceinline__ void wave4_chain(const WaveOps<OP, DILU, FASTDIV, HS>& r, const WaveHalo<OP, FASTDIV, HS>& h, const WaveOut<OP>& out, int t0, int lane,
+                                            int skew, int nx, bool pencil, bool edgeInY, bool edgeInZ, bool hasY, bool hasZ, double& last, double& acc, double& held,
+                                            unsigned& bad, const Slot* Sn = nullptr, int sn0 = 0, WaveOps<OP, DILU, FASTDIV, HS>* nxt = nullptr)
 {
     constexpr bool bwd = OP == 2;
     const unsigned full = 0xffffffffu;
@@ -68,13 +76,14 @@ __device__ __forceinline__ void wave4_chain(const WaveOps<OP, DILU, FASTDIV, HS>
 #pragma unroll
     for (int ss = 0; ss < HS; ss++) {
         const int s = bwd ? HS - 1 - ss : ss;
+        if constexpr (PRE) wave4_fetch_one<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(*Sn, sn0, lane, *nxt, ss);
         bool act = pencil;
         if (RAMP) { const int i = t0 + s - skew; act = act && i >= 0 && i < nx; }
         const double c0 = r.c0[s], c1 = r.c1[s], c2 = r.c2[s], c3 = r.c3[s];
         double vy = bwd ? __shfl_down_sync(full, last, 1) : __shfl_up_sync(full, last, 1);
         double vz = bwd ? __shfl_down_sync(full, last, WTJ) : __shfl_up_sync(full, last, WTJ);
-        vy = edgeInY ? r.hy[s] : vy;
-        vz = edgeInZ ? r.hz[s] : vz;
+        vy = edgeInY ? h.hy[s] : vy;
+        vz = edgeInZ ? h.hz[s] : vz;
         double res;
         if (OP == 0) {
             // rD[u] -= upper*upper/rD[l] (DIC) or upper*lower/rD[l] (DILU), faces ascending: z, y, x lower neighbours
@@ -85,8 +94,8 @@ __device__ __forceinline__ void wave4_chain(const WaveOps<OP, DILU, FASTDIV, HS>
                 const double nz_ = hasZ ? numz : 0.0, ny_ = hasY ? numy : 0.0, nx_ = hasX ? numx : 0.0;
                 double yy = bwd ? __shfl_down_sync(full, held, 1) : __shfl_up_sync(full, held, 1);
                 double yz = bwd ? __shfl_down_sync(full, held, WTJ) : __shfl_up_sync(full, held, WTJ);
-                yy = edgeInY ? r.yY[s] : yy;
-                yz = edgeInZ ? r.yZ[s] : yz;
+                yy = edgeInY ? h.yY[s] : yy;
+                yz = edgeInZ ? h.yZ[s] : yz;
                 tz = div_by(nz_, vz, yz); ty = div_by(ny_, vy, yy); tx = div_by(nx_, last, held);
             } else {
                 tz = (hasZ ? numz : 1.0) / vz; ty = (hasY ? numy : 1.0) / vy; tx = (hasX ? numx : 1.0) / last;
@@ -138,14 +147,22 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
     extern __shared__ __align__(128) unsigned char smemRaw[];
     Smem& sm = *reinterpret_cast<Smem*>(smemRaw);
     __shared__ const double* srcS[8];              // the streamed arrays of this sweep in slot order, indexable by lane
+    // The halo channel: the neighbour tiles' edge elements, step by step (ring over the steps in processing order), and two
+    // progress counters -- steps whose elements have all arrived (halo warp -> compute warp), steps consumed (back-pressure).
+    // Finer than the ring slots on purpose: a slot-sized hand-over made every group wait for a whole poll pass, its hand-over and
+    // the compute warp's wake-up in sequence, which a tile close behind its producer could not sustain at the producer's pace.
+    constexpr int RH = 64;
+    __shared__ double hyRing[RH * WTK], hzRing[RH * WTJ];
+    __shared__ unsigned haloProg, compProg;
     const WaveGeom& g = a.g;
     const unsigned full = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tj = lane & (WTJ - 1), tk = lane / WTJ;
     constexpr bool bwd = OP == 2;
     if (threadIdx.x == 0) {
         sm.tile = atomicAdd(a.ticket, 1);                  // topological hand-out: one tile per CTA
-        // full: the stream warp's arrive.expect_tx (bulk bytes) + the halo warp's arrive; empty: the compute warp's arrive
-        for (int r = 0; r < RNG; r++) { mbar_init(&sm.full[r], 2); mbar_init(&sm.empty[r], 1); }
+        // full: the stream warp's arrive.expect_tx (bulk bytes); empty: the compute warp's arrive.  The halo has its own channel.
+        for (int r = 0; r < RNG; r++) { mbar_init(&sm.full[r], 1); mbar_init(&sm.empty[r], 1); }
+        haloProg = 0u; compProg = 0u;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (OP == 2) { srcS[0] = a.WF; srcS[1] = a.QX; srcS[2] = a.QY; srcS[3] = a.QZ; srcS[4] = a.RF; srcS[5] = a.A0; }
         else if (OP == 1) { srcS[0] = a.A0; srcS[1] = a.PX; srcS[2] = a.PY; srcS[3] = a.PZ; if (WIO) srcS[NARR - 1] = a.RF; }
@@ -215,12 +232,6 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
 #pragma unroll
             for (int r = 0; r < NZ; r++) ld_relaxed_if(z[r], XZp + (size_t)(tb + sZ0 + r * (32 / WTJ)) * 32, valid && is_sentinel(z[r]));
         };
-        auto pending = [&](const double& y, const double (&z)[NZ]) {
-            bool p = is_sentinel(y);
-#pragma unroll
-            for (int r = 0; r < NZ; r++) p = p || is_sentinel(z[r]);
-            return __any_sync(full, p) != 0;
-        };
 #pragma unroll
         for (int q = 0; q < DEPTH; q++) {
             vY[q] = 0.0;
@@ -229,30 +240,53 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
         }
 #pragma unroll
         for (int q = 0; q < DEPTH - 1; q++) if (q < nGroups) first(q, vY[q], vZ[q]);
+        // processing-order offset (within its group) of this lane's elements
+        const int pY = bwd ? GSZ - 1 - sY : sY;
         for (int grp0 = 0; grp0 < nGroups; grp0 += DEPTH) {
 #pragma unroll
             for (int q = 0; q < DEPTH; q++) {
                 const int grp = grp0 + q;
                 if (grp < nGroups) {
                     if (grp + DEPTH - 1 < nGroups) first(grp + DEPTH - 1, vY[(q + DEPTH - 1) % DEPTH], vZ[(q + DEPTH - 1) % DEPTH]);
+                    const int pBase = grp * GSZ;
+                    int delivered = 0;
                     long long c0 = tracing ? clock64() : 0;
-                    while (pending(vY[q], vZ[q])) {
+                    for (;;) {
+                        // leading steps (processing order) of this group whose elements are all here
+                        const unsigned yOk = __ballot_sync(full, !is_sentinel(vY[q]));
+                        unsigned zOk[NZ];
+#pragma unroll
+                        for (int r = 0; r < NZ; r++) zOk[r] = __ballot_sync(full, !is_sentinel(vZ[q][r]));
+                        int k = 0;
+#pragma unroll
+                        for (int i = 0; i < GSZ; i++) {
+                            const int sM = bwd ? GSZ - 1 - i : i;                                    // memory-order offset of processing step i
+                            const bool okY = ((yOk >> (WTK * sM)) & ((1u << WTK) - 1u)) == ((1u << WTK) - 1u);
+                            const bool okZ = ((zOk[sM / (32 / WTJ)] >> (WTJ * (sM % (32 / WTJ)))) & ((1u << WTJ) - 1u)) == ((1u << WTJ) - 1u);
+                            if (okY && okZ && k == i) k = i + 1;
+                        }
+                        if (k > delivered) {
+                            // back-pressure: the ring entries about to be overwritten have been consumed (never waits in practice)
+                            while ((int)ld_acquire_cta_u32(&compProg) + RH < pBase + k) {}
+                            if (lane < NEY && pY >= delivered && pY < k) hyRing[((pBase + pY) & (RH - 1)) * WTK + tkY] = vY[q];
+#pragma unroll
+                            for (int r = 0; r < NZ; r++) {
+                                const int sZ = sZ0 + r * (32 / WTJ);
+                                const int pZ = bwd ? GSZ - 1 - sZ : sZ;
+                                if (sZ < GSZ && pZ >= delivered && pZ < k) hzRing[((pBase + pZ) & (RH - 1)) * WTJ + tjZ] = vZ[q][r];
+                            }
+                            __syncwarp();
+                            if (lane == 0) st_release_cta_u32(&haloProg, (unsigned)(pBase + k));
+                            delivered = k;
+                        }
+                        if (k == GSZ) break;
                         // everything that is missing of every group in flight, oldest first (the youngest group's first loads may
                         // still be on their way: its predicate is evaluated last)
 #pragma unroll
                         for (int d = 0; d < DEPTH; d++) again(grp + d, vY[(q + d) % DEPTH], vZ[(q + d) % DEPTH]);
                         if (tracing) ph[1] += 1;
                     }
-                    if (tracing) { const long long c1 = clock64(); ph[0] += c1 - c0; c0 = c1; }
-                    const int slot = grp % RNG;
-                    mbar_wait(&sm.empty[slot], (((unsigned)(grp / RNG)) & 1u) ^ 1u);          // the compute warp is done with this slot
-                    if (tracing) { const long long c1 = clock64(); ph[2] += c1 - c0; }
-                    Slot& S = sm.slot[slot];
-                    if (lane < NEY) S.hy[smY] = vY[q];
-#pragma unroll
-                    for (int r = 0; r < NZ; r++) { const int sZ = sZ0 + r * (32 / WTJ); if (sZ < GSZ) S.hz[sZ * 32 + smZ] = vZ[q][r]; }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.full[slot]);
+                    if (tracing) { const long long c1 = clock64(); ph[0] += c1 - c0; }
                     if (grp < 5) stamp(grp);
                 }
             }
@@ -327,60 +361,107 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
     out.QX = a.QX + tileBase + lane; out.QY = a.QY + tileBase + lane; out.QZ = a.QZ + tileBase + lane;
     constexpr int HS = GSZ / 2;
     using Ops = WaveOps<OP, DILU, FASTDIV, HS>;
-    const int nUnits = 2 * nGroups;
-    auto slotOf = [&](int u) { return (u >> 1) % RNG; };
-    auto parityOf = [&](int u) { return ((unsigned)((u >> 1) / RNG)) & 1u; };
-    auto s0Of = [&](int u) { return bwd ? (1 - (u & 1)) * HS : (u & 1) * HS; };
-    auto fetch = [&](int u, Ops& r) { wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(sm.slot[slotOf(u)], s0Of(u), lane, r); };
-    auto interiorOf = [&](int u) { const int t0 = tbOf(u >> 1) + s0Of(u); return t0 >= WTJ + WTK - 2 && t0 + HS - 1 < g.nx; };
-    auto chain = [&](int u, const Ops& r, bool interior) {
-        const int t0 = tbOf(u >> 1) + s0Of(u);
-        if (interior) wave4_chain<OP, DILU, DOT, false, WIO, FASTDIV, HS>(r, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
-        else wave4_chain<OP, DILU, DOT, true, WIO, FASTDIV, HS>(r, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
+    // shared-window addresses of the barriers, formed once (the generic-to-shared conversion costs an S2R every time it is redone)
+    const unsigned fullBase = smem_u32(&sm.full[0]), emptyBase = smem_u32(&sm.empty[0]);
+    auto waitFull = [&](int slot, unsigned parity) {
+        asm volatile("{\n\t.reg .pred P1;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                     ::"r"(fullBase + 8u * (unsigned)slot), "r"(parity) : "memory");
     };
-    // one half-slot: the chain of unit u on `cur`, the operands of unit u + 1 into `nxt`
-    auto unit = [&](int u, Ops& cur, Ops& nxt, bool secondHalf) {
-        const int nu = u + 1;
-        const bool haveNext = nu < nUnits;
-        bool pre = haveNext;
-        if (secondHalf && haveNext) pre = __all_sync(full, mbar_test(&sm.full[slotOf(nu)], parityOf(nu)));      // the next slot: only if it is there already
-        const bool interior = interiorOf(u);
-        if (pre && interior) {
-            fetch(nu, nxt);                    // same basic block as the chain below: scheduled into its stall slots
-            wave4_chain<OP, DILU, DOT, false, WIO, FASTDIV, HS>(cur, out, tbOf(u >> 1) + s0Of(u), lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
-        } else {
-            chain(u, cur, interior);
+    auto testFull = [&](int slot, unsigned parity) {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred P1;\n\tmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n\tselp.u32 %0, 1, 0, P1;\n\t}"
+                     : "=r"(ok) : "r"(fullBase + 8u * (unsigned)slot), "r"(parity) : "memory");
+        return ok != 0;
+    };
+    auto arriveEmpty = [&](int slot) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(emptyBase + 8u * (unsigned)slot) : "memory"); };
+    // state of the walk over the ring: the slot and phase parity of the group in hand (no modulo in the loop)
+    int slot = 0; unsigned parity = 0u;
+    int tb = tbOf(0);
+    using Halo = WaveHalo<OP, FASTDIV, HS>;
+    int pDone = 0;                                // steps completed, processing order
+    // the halo of the next HS steps: wait until the halo warp has delivered them, then ring -> registers
+    auto fetchHalo = [&](Halo& h, int t0) {
+        const unsigned need = (unsigned)(pDone + HS);
+        if (ld_acquire_cta_u32(&haloProg) < need) {
+            const long long c0 = tracing ? clock64() : 0;
+            while (ld_acquire_cta_u32(&haloProg) < need) {}
+            if (tracing) ph[1] += clock64() - c0;
+        }
+#pragma unroll
+        for (int s = 0; s < HS; s++) {
+            const int p = bwd ? g.nStepsPad - 1 - (t0 + s) : t0 + s;
+            h.hy[s] = hyRing[(p & (RH - 1)) * WTK + tk];
+            h.hz[s] = hzRing[(p & (RH - 1)) * WTJ + tj];
+            if (OP == 0 && FASTDIV) { h.yY[s] = div_refine(h.hy[s]); h.yZ[s] = div_refine(h.hz[s]); }
+        }
+    };
+    auto halfDone = [&]() {
+        pDone += HS;
+        __syncwarp();
+        if (lane == 0) st_release_cta_u32(&compProg, (unsigned)pDone);
+    };
+    // first half of group `grp` (operands in `cur`), prefetching the second half of the same slot
+    auto firstHalf = [&](int grp, Ops& cur, Ops& nxt) {
+        const Slot& S = sm.slot[slot];
+        const int s0 = bwd ? HS : 0, sn0 = bwd ? 0 : HS;
+        const int t0 = tb + s0;
+        Halo h;
+        fetchHalo(h, t0);
+        if (t0 >= WTJ + WTK - 2 && t0 + HS - 1 < g.nx)
+            wave4_chain<OP, DILU, DOT, false, WIO, FASTDIV, HS, true, NARR, Slot>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad, &S, sn0, &nxt);
+        else {
+            wave4_chain<OP, DILU, DOT, true, WIO, FASTDIV, HS>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
+            wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(S, sn0, lane, nxt);
+        }
+        halfDone();
+    };
+    // second half of group `grp`; the first half of the next group is prefetched only if its slot has landed already
+    auto secondHalf = [&](int grp, Ops& cur, Ops& nxt) {
+        const int s0 = bwd ? 0 : HS, sn0 = bwd ? HS : 0;
+        const int t0 = tb + s0;
+        const bool haveNext = grp + 1 < nGroups;
+        const int nslot = slot + 1 == RNG ? 0 : slot + 1;
+        const unsigned nparity = slot + 1 == RNG ? parity ^ 1u : parity;
+        const Slot& Sn = sm.slot[nslot];
+        Halo h;
+        fetchHalo(h, t0);
+        const bool pre = haveNext && __all_sync(full, testFull(nslot, nparity));
+        const bool interior = t0 >= WTJ + WTK - 2 && t0 + HS - 1 < g.nx;
+        if (pre && interior)
+            wave4_chain<OP, DILU, DOT, false, WIO, FASTDIV, HS, true, NARR, Slot>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad, &Sn, sn0, &nxt);
+        else {
+            if (interior) wave4_chain<OP, DILU, DOT, false, WIO, FASTDIV, HS>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
+            else wave4_chain<OP, DILU, DOT, true, WIO, FASTDIV, HS>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
             if (haveNext) {
                 if (!pre) {
                     const long long c0 = tracing ? clock64() : 0;
-                    mbar_wait(&sm.full[slotOf(nu)], parityOf(nu));
+                    waitFull(nslot, nparity);
                     if (tracing) ph[0] += clock64() - c0;
                 }
-                fetch(nu, nxt);
+                wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(Sn, sn0, lane, nxt);
             }
         }
-        if (secondHalf) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.empty[slotOf(u)]);
-            const int grp = u >> 1;
-            if (grp < 5) stamp(5 + grp);
-            if (grp == nGroups - 1) stamp(10);
-        }
+        halfDone();
+        if (lane == 0) arriveEmpty(slot);
+        if (grp < 5) stamp(5 + grp);
+        if (grp == nGroups - 1) stamp(10);
+        slot = nslot; parity = nparity;
+        tb += bwd ? -GSZ : GSZ;
     };
     Ops opsA, opsB;
     const long long cStart = tracing ? clock64() : 0;
-    mbar_wait(&sm.full[0], 0u);
-    fetch(0, opsA);
-    for (int u = 0; u < nUnits; u += 2) {
-        unit(u, opsA, opsB, false);
-        unit(u + 1, opsB, opsA, true);
+    waitFull(0, 0u);
+    wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(sm.slot[0], bwd ? HS : 0, lane, opsA);
+    for (int grp = 0; grp < nGroups; grp++) {
+        firstHalf(grp, opsA, opsB);
+        secondHalf(grp, opsB, opsA);
     }
     if (DOT) {
         acc = warp_reduce<Sum>(acc);
         if (lane == 0) a.tilePartial[T] = acc;
     }
     if (OP == 0 && FASTDIV && __any_sync(full, bad != 0) && lane == 0) atomicOr(a.ticket + 1, 1);
-    if (tracing && lane == 0) { a.trace[WTRACE * T + 20] = ph[0]; a.trace[WTRACE * T + 21] = clock64() - cStart - ph[0]; }
+    if (tracing && lane == 0) { a.trace[WTRACE * T + 20] = ph[0] + ph[1]; a.trace[WTRACE * T + 21] = clock64() - cStart - ph[0] - ph[1]; a.trace[WTRACE * T + 22] = ph[1]; }
 }
 
 } // namespace b200

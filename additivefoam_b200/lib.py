@@ -24,7 +24,7 @@ REDUCE_FN = C.CFUNCTYPE(C.c_double, C.c_double, C.c_void_p)      # b200_reduce_s
 
 #: every symbol include/additivefoam_b200.h declares
 SYMBOLS = [
-    "b200_last_error", "b200_abi_version", "b200_nccl_unique_id", "b200_ctx_create", "b200_ctx_destroy",
+    "b200_last_error", "b200_abi_version", "b200_device_count", "b200_nccl_unique_id", "b200_ctx_create", "b200_ctx_destroy",
     "b200_ctx_peer_export", "b200_ctx_peer_export_halo", "b200_ctx_peer_import", "b200_ctx_synchronize", "b200_ctx_mark", "b200_ctx_elapsed_ms", "b200_profile_enable", "b200_profile_groups",
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",

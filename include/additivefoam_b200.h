@@ -174,6 +174,8 @@ int  b200_abi_version(void);
 /* One context per process = one GPU = one subdomain (the reference's one MPI rank).
  * nccl_unique_id: 128-byte ncclUniqueId shared by all ranks, or NULL when nranks == 1. */
 int  b200_nccl_unique_id(void* out128);
+/* Number of CUDA devices visible to this process (a shim picks its device from it and the node-local rank). */
+int  b200_device_count(int* count);
 int  b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, int nranks, b200_ctx** out);
 int  b200_ctx_destroy(b200_ctx* ctx);
 /* Optional, ranks of one node: replace the NCCL all-reduces of scalars by a peer-memory (NVLink) mailbox exchange.

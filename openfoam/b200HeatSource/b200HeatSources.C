@@ -18,12 +18,32 @@ namespace heatSourceModels
 
 static b200_ctx* b200HeatCtx()
 {
+    // one context per process; in a parallel run the ranks of a node share its GPUs round-robin.  No communicator is needed:
+    // the only global quantity, the normalisation sum of heatSourceModel.C:359, goes through Foam::reduce (b200ReduceSum)
     static b200_ctx* c = nullptr;
-    if (!c && b200_ctx_create(0, nullptr, 0, 1, &c) != 0)
+    if (!c)
     {
-        FatalErrorInFunction << b200_last_error() << Foam::exit(Foam::FatalError);
+        int nDevices = 1;
+        if (b200_device_count(&nDevices) != 0 || nDevices < 1)
+        {
+            FatalErrorInFunction << b200_last_error() << Foam::exit(Foam::FatalError);
+        }
+        const int device = Foam::Pstream::parRun() ? Foam::Pstream::myProcNo() % nDevices : 0;
+        if (b200_ctx_create(device, nullptr, 0, 1, &c) != 0)
+        {
+            FatalErrorInFunction << b200_last_error() << Foam::exit(Foam::FatalError);
+        }
     }
     return c;
+}
+
+
+// fvc::domainIntegrate's reduction (heatSourceModel.C:359) for b200_beam_qdot_sub
+static double b200ReduceSum(double local, void*)
+{
+    Foam::scalar s = local;
+    Foam::reduce(s, Foam::sumOp<Foam::scalar>());
+    return s;
 }
 
 
@@ -45,23 +65,47 @@ Foam::heatSourceModels::b200HeatSource::b200HeatSource
     beam_.absorptionModel = B200_ABSORPTION_CONSTANT;
     beam_.hitPathIntervals = 1;
 
-    // a uniform single block: spacing from the first cell centre, counts from the bounding box
-    const boundBox bb(mesh.points(), false);
+    // This rank's cells must be a sub-block of ONE uniform blockMesh hex block, in blockMesh cell order (x fastest): the whole
+    // block in a serial run, one piece of a `simple` / `hierarchical` decomposition in a parallel one (decomposePar keeps the
+    // cell order within a rank).  Spacing from the first cell centre, counts from the bounding boxes.
+    const boundBox bbGlobal(mesh.points(), true);       // reduced over the ranks
+    const boundBox bbLocal(mesh.points(), false);
     const vector c0 = mesh.cellCentres()[0];
-    label n[3];
+    vector spacing;
     for (direction d = 0; d < 3; d++)
     {
-        const scalar spacing = 2.0*(c0[d] - bb.min()[d]);
-        n[d] = label(round(bb.span()[d]/spacing));
-        block_.min[d] = bb.min()[d];
-        block_.max[d] = bb.max()[d];
+        spacing[d] = 2.0*(c0[d] - bbLocal.min()[d]);
+        block_.min[d] = bbGlobal.min()[d];
+        block_.max[d] = bbGlobal.max()[d];
+        nLocal_[d] = int32_t(round(bbLocal.span()[d]/spacing[d]));
+        offset_[d] = int32_t(round((bbLocal.min()[d] - bbGlobal.min()[d])/spacing[d]));
     }
-    block_.nx = n[0]; block_.ny = n[1]; block_.nz = n[2];
+    block_.nx = int32_t(round(bbGlobal.span()[0]/spacing[0]));
+    block_.ny = int32_t(round(bbGlobal.span()[1]/spacing[1]));
+    block_.nz = int32_t(round(bbGlobal.span()[2]/spacing[2]));
 
-    if (n[0]*n[1]*n[2] != mesh.nCells() || Pstream::parRun())
+    bool ok = label(nLocal_[0])*nLocal_[1]*nLocal_[2] == mesh.nCells();
+    if (ok)
+    {
+        // the last cell and one in the middle sit where the closed form i + nx*(j + ny*k) puts them
+        const label probes[2] = {mesh.nCells() - 1, mesh.nCells()/2};
+        for (int q = 0; q < 2; q++)
+        {
+            const label c = probes[q];
+            const label ijk[3] = {c % nLocal_[0], (c/nLocal_[0]) % nLocal_[1], c/(nLocal_[0]*nLocal_[1])};
+            for (direction d = 0; d < 3; d++)
+            {
+                const scalar expected = bbLocal.min()[d] + (ijk[d] + 0.5)*spacing[d];
+                ok = ok && mag(mesh.cellCentres()[c][d] - expected) < 1e-6*spacing[d];
+            }
+        }
+    }
+    reduce(ok, andOp<bool>());
+    if (!ok)
     {
         FatalErrorInFunction
-            << type << " needs a serial run on a single uniform blockMesh hex block"
+            << type << " needs a mesh that is one uniform blockMesh hex block, undecomposed or cut by the"
+            << " simple / hierarchical method (each rank a sub-block in blockMesh cell order)"
             << exit(FatalError);
     }
 }
@@ -129,9 +173,10 @@ Foam::tmp<Foam::volScalarField> Foam::heatSourceModels::b200HeatSource::qDot()
     double sumWeights, volume, absorbed;
     if
     (
-        b200_beam_qdot
+        b200_beam_qdot_sub
         (
-            b200HeatCtx(), &block_, &currentBeam(), pos, dims, movingBeam_->power(),
+            b200HeatCtx(), &block_, offset_, nLocal_, &currentBeam(), pos, dims, movingBeam_->power(),
+            Pstream::parRun() ? &b200ReduceSum : nullptr, nullptr,
             q.primitiveFieldRef().begin(), &sumWeights, &volume, &absorbed
         ) != 0
     )

@@ -19,6 +19,12 @@
 #include "superGaussian.C"
 #include "modifiedSuperGaussian.C"
 #include "projectedGaussian.C"
+#ifdef REF_MHS_WITH_B200
+// oracle/_ref/refMHSb200: the GPU shim of the drop-in seam B2 compiled into the same world, so that the reference's own run-time
+// selection (heatSourceModelNew.C) constructs it by its TypeName and movingHeatSourceModel::update() drives it (kinds b200super,
+// b200modified, b200projected).  Links the product library: runs on the GPU box only (tests/test_gpu_shim_exec.py).
+#include "b200HeatSources.C"
+#endif
 
 #include <iostream>
 
@@ -50,7 +56,10 @@ int main()
             std::string name, kind, k, m, A, B, dx, dy, dz, npx, npy, npz, file;
             std::string eta; double beamDt; int hit;
             std::cin >> name >> kind >> k >> m >> A >> B >> dx >> dy >> dz >> npx >> npy >> npz >> eta >> beamDt >> hit >> file;
-            const std::string type = kind == "super" ? "superGaussian" : kind == "modified" ? "modifiedSuperGaussian" : "projectedGaussian";
+            const bool gpu = kind.rfind("b200", 0) == 0;
+            const std::string base = gpu ? kind.substr(4) : kind;
+            std::string type = base == "super" ? "superGaussian" : base == "modified" ? "modifiedSuperGaussian" : "projectedGaussian";
+            if (gpu) type = "b200" + std::string(1, (char)std::toupper(type[0])) + type.substr(1);
             const std::string p = name + ".", c = name + "." + type + "Coeffs.";
             refEntries()[p + "heatSourceModel"] = type;
             refEntries()[c + "k"] = k; refEntries()[c + "m"] = m; refEntries()[c + "A"] = A; refEntries()[c + "B"] = B;

@@ -57,19 +57,22 @@ def path_text(rows):
     return "Mode X Y Z Power Param\n" + "".join(" ".join(repr(float(v)) if i else str(int(v)) for i, v in enumerate(r)) + "\n" for r in rows)
 
 
-def run(cfg, tmp):
+def run(cfg, tmp, exe=REF, kind_prefix=""):
+    """exe / kind_prefix: tests/test_gpu_shim_exec.py replays the same requests through oracle/_ref/refMHSb200 with the GPU shim's types."""
     m = MESH
     lines = ["mhs %d %d %d %r %r %r %r %r %r  %r %r  %d %d" % (*m["n"], *m["min"], *m["max"], cfg["start"], cfg["end"], len(cfg["beams"]), len(cfg["steps"]))]
     for b in cfg["beams"]:
         f = os.path.join(tmp, b["name"] + ".path")
         with open(f, "w") as fh:
             fh.write(path_text(b["path"]))
-        lines.append("%s %s %r %r %r %r  %r %r %r  %d %d %d  %r  %r %d %s" % (b["name"], b["kind"], b["k"], b["m"], b["A"], b["B"], *b["dims"], *b["nPoints"],
+        lines.append("%s %s %r %r %r %r  %r %r %r  %d %d %d  %r  %r %d %s" % (b["name"], kind_prefix + b["kind"], b["k"], b["m"], b["A"], b["B"], *b["dims"], *b["nPoints"],
                                                                              b["eta"], b["deltaT"] if b["deltaT"] > 0 else -1.0, b["hit"], f))
         if b["kelly"]:
             lines[-1] = lines[-1].replace("  %r  " % b["eta"], "  kelly:%s:%r:%r  " % tuple(b["kelly"]), 1)
     lines += [repr(dt) for dt in cfg["steps"]]
-    out = subprocess.run([REF], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    res = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True)
+    assert res.returncode == 0, (res.returncode, res.stderr[-2000:])
+    out = res.stdout.split("\n")
     out = [ln for ln in out if ln]
     steps, i = [], 0
     for _ in cfg["steps"]:
