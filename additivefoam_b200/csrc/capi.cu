@@ -381,6 +381,14 @@ int b200_case_set_field(b200_case* c, int32_t field, const double* in)
     c->p->setField(field, in);
     B200_CATCH
 }
+int b200_case_reset_alpha_solid(b200_case* c)
+{
+    B200_TRY
+    B200_CHECK(c != nullptr, "reset_alpha_solid: bad arguments");
+    B200_CUDA(cudaSetDevice(c->p->ctx->device));
+    c->p->resetAlphaSolidFromT();
+    B200_CATCH
+}
 int b200_case_set_field_async(b200_case* c, int32_t field, const double* pinnedIn)
 {
     B200_TRY
@@ -493,8 +501,10 @@ int b200_scan_path_parse(const char* text, double* out, int32_t maxSegments)
         std::stringstream ls(line);
         double v[6] = {0, 0, 0, 0, 0, 0};
         ls >> v[0] >> v[1] >> v[2] >> v[3] >> v[4] >> v[5];
-        if (n >= maxSegments) return -1;
-        for (int q = 0; q < 6; q++) out[6 * n + q] = v[q];
+        if (out != nullptr) {                      // out == NULL: count only
+            if (n >= maxSegments) return -1;
+            for (int q = 0; q < 6; q++) out[6 * n + q] = v[q];
+        }
         n++;
     }
     return n;

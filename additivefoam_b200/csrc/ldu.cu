@@ -146,7 +146,7 @@ Ldu::~Ldu()
     for (auto& p : stage) dev_free(p);
     for (auto& p : stageBou) dev_free(p);
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]); dev_free(waveOrderC[2]);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveTraceG); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]); dev_free(waveOrderC[2]);
     dev_free(d_fStart); dev_free(d_fPos); dev_free(d_fFace); dev_free(d_bStart); dev_free(d_bPos); dev_free(d_bFace);
     dev_free(flowCoefF); dev_free(flowCoefB); dev_free(flowNumF); dev_free(flowRD); dev_free(flowF); dev_free(flowB);
     dev_free(flowPartial); dev_free(flowTicket);
@@ -157,8 +157,9 @@ void Ldu::setBlock(int nx, int ny, int nz)
     BlockDims d; d.nx = nx; d.ny = ny; d.nz = nz;
     B200_CHECK(nx > 0 && ny > 0 && nz > 0, "block dimensions must be positive");
     B200_CHECK(d.nCells() == nCells && d.nFaces() == nFaces, "block dimensions do not match nCells/nFaces");
-    B200_CHECK(ifaces.empty(), "the block kernels take their coupled neighbours from ghost planes (resident stepper); a decomposed "
-                               "OpenFOAM mesh keeps the general addressing path");
+    // Coupled interfaces (one rank of a decomposed OpenFOAM case whose sub-domain is a block: `simple` / `hierarchical` decomposition
+    // of a blockMesh block): the block kernels do the interior -- Amul without ghost planes, the block-local DIC/DILU sweeps of
+    // [UPSTREAM] processor boundaries -- and the interface contributions are applied after the gather, as on general addressing.
     // expand the closed form on the device and compare bit-exactly with the addressing given at creation
     int* lo = dev_alloc<int>(nFaces); int* up = dev_alloc<int>(nFaces);
     k_block_addressing<<<std::min(ny * nz, 4096), BLK, 0, ctx->stream>>>(d, lo, up);
@@ -175,7 +176,7 @@ void Ldu::setBlock(int nx, int ny, int nz)
     dev_free(rD);
     // the wave-order arrays, the tile order and the gathered coefficients belong to the block shape
     for (auto& p : wave) dev_free(p);
-    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]); dev_free(waveOrderC[2]);
+    dev_free(waveFlags); dev_free(wavePartial); dev_free(waveOrder); dev_free(waveTrace); dev_free(waveTraceG); dev_free(waveOrderC[0]); dev_free(waveOrderC[1]); dev_free(waveOrderC[2]);
     waveEpoch = -1; waveUpper = nullptr; waveLower = nullptr;
 }
 
@@ -403,11 +404,19 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     a.WF = wave[7]; a.RF = wave[8]; a.WB = wave[9]; a.NX = wave[10]; a.NY = wave[11]; a.NZ = wave[12]; a.DG = wave[13];
     a.rA = rA; a.wA = wA;
     a.ticket = waveFlags; a.order = waveOrder; a.tilePartial = wavePartial; a.st = d_state;
-    a.trace = nullptr; a.nCtas = 0; a.orderC = nullptr;
+    a.trace = nullptr; a.traceG = nullptr; a.nCtas = 0; a.orderC = nullptr;
+    { static const int hd = [] { const char* e = std::getenv("B200_WAVE4_DEPTH"); return e ? std::atoi(e) : 1; }(); a.haloDepth = hd; }
     static const bool traceOn = [] { const char* e = std::getenv("B200_WAVE_TRACE"); return e && std::atoi(e) != 0; }();
     if (traceOn) {
         if (!waveTrace) { waveTrace = dev_alloc<long long>((size_t)a.g.nTiles * WTRACE); B200_CUDA(cudaMemsetAsync(waveTrace, 0, (size_t)a.g.nTiles * WTRACE * sizeof(long long), ctx->stream)); }
         a.trace = waveTrace;
+        static const bool traceAll = [] { const char* e = std::getenv("B200_WAVE_TRACE"); return e && std::atoi(e) >= 2; }();
+        if (traceAll) {
+            const size_t nG = (size_t)a.g.nTiles * (a.g.nStepsPad / 4);
+            if (!waveTraceG) waveTraceG = dev_alloc<long long>(nG);
+            B200_CUDA(cudaMemsetAsync(waveTraceG, 0, nG * sizeof(long long), ctx->stream));
+            a.traceG = waveTraceG;
+        }
     }
     {
         // keep what the resident tiles have prefetched but not yet consumed well inside L2 (126 MB): about 32 MB in flight
@@ -455,18 +464,18 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         const int cfg = eg ? std::atoi(eg) : (a.g.nTiles > 1536 ? 83 : 86);
 #define B200_W4(G_, R_)                                                                                                                        \
         do {                                                                                                                                   \
-            if (op == 0) { if (dilu) launch4(k_wave4<0, true, false, true, true, G_, R_>, sizeof(WaveSmem<0, true, true, G_, R_>));                     \
-                           else launch4(k_wave4<0, false, false, true, true, G_, R_>, sizeof(WaveSmem<0, false, true, G_, R_>)); }                      \
-            else if (op == 1) { if (wio) launch4(k_wave4<1, false, false, true, false, G_, R_>, sizeof(WaveSmem<1, false, true, G_, R_>));               \
-                                else launch4(k_wave4<1, false, false, false, false, G_, R_>, sizeof(WaveSmem<1, false, false, G_, R_>)); }               \
-            else if (wio) { if (dot) launch4(k_wave4<2, false, true, true, false, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>));                    \
-                            else launch4(k_wave4<2, false, false, true, false, G_, R_>, sizeof(WaveSmem<2, false, true, G_, R_>)); }                     \
-            else if (dot) launch4(k_wave4<2, false, true, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                             \
-            else launch4(k_wave4<2, false, false, false, false, G_, R_>, sizeof(WaveSmem<2, false, false, G_, R_>));                                     \
+            if (op == 0) { if (dilu) launch4(k_wave4<0, true, false, true, true, G_, R_>, sizeof(WaveSmem4<0, true, true, G_, R_>));                     \
+                           else launch4(k_wave4<0, false, false, true, true, G_, R_>, sizeof(WaveSmem4<0, false, true, G_, R_>)); }                      \
+            else if (op == 1) { if (wio) launch4(k_wave4<1, false, false, true, false, G_, R_>, sizeof(WaveSmem4<1, false, true, G_, R_>));               \
+                                else launch4(k_wave4<1, false, false, false, false, G_, R_>, sizeof(WaveSmem4<1, false, false, G_, R_>)); }               \
+            else if (wio) { if (dot) launch4(k_wave4<2, false, true, true, false, G_, R_>, sizeof(WaveSmem4<2, false, true, G_, R_>));                    \
+                            else launch4(k_wave4<2, false, false, true, false, G_, R_>, sizeof(WaveSmem4<2, false, true, G_, R_>)); }                     \
+            else if (dot) launch4(k_wave4<2, false, true, false, false, G_, R_>, sizeof(WaveSmem4<2, false, false, G_, R_>));                             \
+            else launch4(k_wave4<2, false, false, false, false, G_, R_>, sizeof(WaveSmem4<2, false, false, G_, R_>));                                     \
             if (op == 0) {                                                                                                                     \
                 k_wave_refactor_prepare<<<ctx->smCount * 4, 256, 0, s>>>(a, waveLen);                                                          \
-                if (dilu) launch4(k_wave4<0, true, false, true, false, G_, R_>, sizeof(WaveSmem<0, true, true, G_, R_>));                                \
-                else launch4(k_wave4<0, false, false, true, false, G_, R_>, sizeof(WaveSmem<0, false, true, G_, R_>));                                   \
+                if (dilu) launch4(k_wave4<0, true, false, true, false, G_, R_>, sizeof(WaveSmem4<0, true, true, G_, R_>));                                \
+                else launch4(k_wave4<0, false, false, true, false, G_, R_>, sizeof(WaveSmem4<0, false, true, G_, R_>));                                   \
             }                                                                                                                                  \
         } while (0)
         if (cfg == 83) B200_W4(8, 3);
@@ -555,6 +564,19 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
         ctx->sync();
         long long t0 = h[11];
         for (int t = 0; t < a.g.nTiles; t++) t0 = std::min(t0, h[WTRACE * t + 11]);
+        if (a.traceG) {         // every group of every tile of the first K-row and of the middle column: where the lag between tiles grows
+            const int nG = a.g.nStepsPad / 8;
+            std::vector<long long> hg((size_t)a.g.nTiles * (a.g.nStepsPad / 4));
+            d2h(hg.data(), waveTraceG, hg.size(), s);
+            ctx->sync();
+            std::fprintf(stderr, "WAVE_GROUPS op %d nJ %d nK %d nG %d\n", op, a.g.nJ, a.g.nK, nG);
+            for (int t = 0; t < a.g.nTiles; t++) {
+                if (t / a.g.nJ != 0 && t % a.g.nJ != a.g.nJ / 2 && t / a.g.nJ != a.g.nK - 1) continue;
+                std::fprintf(stderr, "WG %d %d", t % a.g.nJ, t / a.g.nJ);
+                for (int q = 0; q < nG; q++) std::fprintf(stderr, " %lld", hg[(size_t)t * nG + q] ? hg[(size_t)t * nG + q] - t0 : -1);
+                std::fprintf(stderr, "\n");
+            }
+        }
         std::fprintf(stderr, "WAVE_TRACE op %d nJ %d nK %d\n", op, a.g.nJ, a.g.nK);
         for (int t = 0; t < a.g.nTiles; t++) {
             std::fprintf(stderr, "WT %d %d", t % a.g.nJ, t / a.g.nJ);
@@ -757,12 +779,11 @@ SolvePerf Ldu::solve(const MatrixView& A, const double* source, double* psi, con
     // fused into the kernel that completes the sum (reduceCtrl / redFor).
     amulFused(A, psi, wA, AM_SUMX, nullptr, C_AVG);
     reduceCtrl(S_SUMPSI, 1, C_AVG);
-    if (isBlock) {
+    if (isBlock && ifaces.empty()) {
         const double* bb = (ghostBelow && A.bouCoeffs) ? A.bouCoeffs[0] : nullptr;
         const double* ba = (ghostAbove && A.bouCoeffs) ? A.bouCoeffs[ghostBelow ? 1 : 0] : nullptr;
         const int64_t items = (int64_t)((dims.nx + BLK - 1) / BLK) * dims.ny * dims.nz;
         const int grid = (int)std::min<int64_t>(items, ctx->persistentBlocks());
-        B200_CHECK(ifaces.empty(), "block addressing with general interfaces: use ghost planes");
         ProfScope ps_(ctx, PC_NORMFACTOR);
         k_normfactor_block<<<grid, BLK, 0, s>>>(dims, A.diag, A.upper, A.lower, bb, ba, source, wA, rA, redFor(C_INIT), st);
         B200_LAUNCH_CHECK();

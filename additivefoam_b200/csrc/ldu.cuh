@@ -114,6 +114,7 @@ public:
     int* waveOrder = nullptr;        // ticket -> tile
     int* waveOrderC[3] = {nullptr, nullptr, nullptr};   // ticket -> CTA tile of k_wave3 (4 / 2 / 1 tiles per CTA)
     long long* waveTrace = nullptr;  // B200_WAVE_TRACE diagnostic
+    long long* waveTraceG = nullptr;
     double* wavePartial = nullptr;
     int64_t waveLen = 0;
     int waveEpoch = -1; const double *waveUpper = nullptr, *waveLower = nullptr; bool waveDilu = false;

@@ -204,6 +204,17 @@ void ThermalCase::setField(int fIn, const double* in)
     ctx->sync();
 }
 
+// Restart (createFields.H:31-44,74-78): alpha.solid is not a file of the case -- it is rebuilt from T
+void ThermalCase::resetAlphaSolidFromT()
+{
+    const int64_t n = dims.nCells();
+    k_alpha_from_T<<<flat_grid(ctx, n), BLK, 2 * (size_t)mat.nThermo * sizeof(double), ctx->stream>>>(n, T, d_thermo, mat.nThermo, alpha1, alpha1old);
+    B200_LAUNCH_CHECK();
+    double a, b2, c2;
+    updatePropertiesAndNumbers(a, b2, c2);            // createFields.H:112 #include "updateProperties.H"
+    ctx->sync();
+}
+
 // ---- streamed host I/O.  The host side of a step is then: inputs of the NEXT step cross PCIe on `h2dStream` while this step's
 // kernels run, results of THIS step cross on `d2hStream` while the next step's kernels run; the compute stream only pays two
 // device-to-device copies per field.  Host buffers must be pinned (cudaMemcpyAsync from pageable memory would serialise).

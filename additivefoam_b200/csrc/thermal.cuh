@@ -65,6 +65,7 @@ public:
     void step(b200_step_report* rep);
     int64_t nLocal() const { return dims.nCells(); }
     int64_t nGlobal() const { return (int64_t)dims.nx * dims.ny * nzGlobal; }
+    void resetAlphaSolidFromT();
     void getField(int field, double* out);
     void setField(int field, const double* in);
     // streamed host I/O (b200_case_set_field_async / apply_staged / get_field_async / transfers_wait)

@@ -372,6 +372,35 @@ __global__ void __launch_bounds__(BLK) k_alpha_update(int64_t n, const double* _
     grid_reduce<1>(v, ops, red, R_RESID, smem);
 }
 
+// createFields.H:74-78 (also what a restart does, :31-44: alpha.solid is never read): alpha.solid = min(max(interpolateXY(T, thermo.x,
+// thermo.y), 0), 1) with SOLVER/interpolateXY/interpolateXY.C:33-109 -- the linear scans that tolerate unsorted abscissae
+__global__ void __launch_bounds__(BLK) k_alpha_from_T(int64_t n, const double* __restrict__ T, const double* __restrict__ thermo, int nT,
+                                                      double* __restrict__ alpha1, double* __restrict__ alpha1old)
+{
+    extern __shared__ double s_tab[];           // x[0..nT) then y[0..nT)
+    for (int q = threadIdx.x; q < 2 * nT; q += BLK) s_tab[q] = thermo[q];
+    __syncthreads();
+    const double* xOld = s_tab; const double* yOld = s_tab + nT;
+    for (int64_t c = blockIdx.x * (int64_t)BLK + threadIdx.x; c < n; c += (int64_t)gridDim.x * BLK) {
+        const double x = T[c];
+        int lo = 0;
+        for (lo = 0; lo < nT && xOld[lo] > x; ++lo) {}
+        const int low = lo;
+        if (low < nT) for (int i = low; i < nT; ++i) if (xOld[i] > xOld[lo] && xOld[i] <= x) lo = i;
+        int hi = 0;
+        for (hi = 0; hi < nT && xOld[hi] < x; ++hi) {}
+        const int high = hi;
+        if (high < nT) for (int i = high; i < nT; ++i) if (xOld[i] < xOld[hi] && xOld[i] >= x) hi = i;
+        double y;
+        if (lo < nT && hi < nT && lo != hi) y = yOld[lo] + ((x - xOld[lo]) / (xOld[hi] - xOld[lo])) * (yOld[hi] - yOld[lo]);
+        else if (lo == hi) y = yOld[lo];
+        else if (lo == nT) y = yOld[hi];
+        else y = yOld[lo];
+        const double a = fmin(fmax(y, 0.0), 1.0);
+        alpha1[c] = a; alpha1old[c] = a;
+    }
+}
+
 // fvc::domainIntegrate(qDot) (solutionControls.H:16)
 __global__ void __launch_bounds__(BLK) k_power(int64_t n, const double* __restrict__ q, double V, RedWork red)
 {

@@ -134,16 +134,29 @@ __device__ __forceinline__ void wave4_chain(const WaveOps<OP, DILU, FASTDIV, HS>
     }
 }
 
+// ring slot of k_wave4: the streamed arrays (+ the natural-order input where there is one); the halo has its own channel
+template <int NARR, int GSZ, bool NEEDIN> struct alignas(128) WaveSlot4 {
+    double arr[NARR][GSZ * 32];
+    double in[NEEDIN ? GSZ * 32 : 16];
+};
+template <int OP, bool DILU, bool WIO, int GSZ, int RNG> struct WaveSmem4 {
+    static constexpr int NARR = OP == 0 ? (DILU ? 6 : 3) + (WIO ? 1 : 0) : (OP == 1 ? (WIO ? 5 : 4) : 6);
+    static constexpr bool NEEDIN = !WIO && OP != 2;
+    WaveSlot4<NARR, GSZ, NEEDIN> slot[RNG];
+    unsigned long long full[RNG], empty[RNG];
+    int tile;
+};
+
 template <int OP, bool DILU, bool DOT, bool WIO, bool FASTDIV, int GSZ, int RNG>
 __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4(WaveArgs a)
 {
     if (a.st != nullptr && a.st->done) return;
     if (OP == 0 && FASTDIV && a.ticket[2] != 0) return;
     if (OP == 0 && !FASTDIV && a.ticket[1] == 0) return;
-    using Smem = WaveSmem<OP, DILU, WIO, GSZ, RNG>;
+    using Smem = WaveSmem4<OP, DILU, WIO, GSZ, RNG>;
     constexpr int NARR = Smem::NARR;
-    using Slot = WaveSlot<NARR, GSZ>;
-    constexpr bool NEEDIN = OP != 2 && !WIO;       // natural-order residual (forward) / matrix diagonal (factor)
+    using Slot = WaveSlot4<NARR, GSZ, Smem::NEEDIN>;
+    constexpr bool NEEDIN = Smem::NEEDIN;          // natural-order residual (forward) / matrix diagonal (factor)
     extern __shared__ __align__(128) unsigned char smemRaw[];
     Smem& sm = *reinterpret_cast<Smem*>(smemRaw);
     __shared__ const double* srcS[8];              // the streamed arrays of this sweep in slot order, indexable by lane
@@ -238,8 +251,14 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
 #pragma unroll
             for (int r = 0; r < NZ; r++) vZ[q][r] = 0.0;
         }
+        // How many groups ahead the first loads go (1 = none ahead, at most DEPTH).  NOT "the more the better": loads that go out
+        // before the producer has written come back as the sentinel and cost a retry, and a consumer that retries is slower than
+        // its producer -- it falls back until its early loads succeed.  The look-ahead distance is therefore the lag a tile settles
+        // at behind its producer (profiles/r2_wave_trace.md: 4.4 us per hop with 4 groups, all tiles at the same pace so that the
+        // lag never shrinks again).
+        const int hd = a.haloDepth < 1 ? 1 : a.haloDepth > DEPTH ? DEPTH : a.haloDepth;
 #pragma unroll
-        for (int q = 0; q < DEPTH - 1; q++) if (q < nGroups) first(q, vY[q], vZ[q]);
+        for (int q = 0; q < DEPTH - 1; q++) if (q < hd - 1 && q < nGroups) first(q, vY[q], vZ[q]);
         // processing-order offset (within its group) of this lane's elements
         const int pY = bwd ? GSZ - 1 - sY : sY;
         for (int grp0 = 0; grp0 < nGroups; grp0 += DEPTH) {
@@ -247,7 +266,9 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
             for (int q = 0; q < DEPTH; q++) {
                 const int grp = grp0 + q;
                 if (grp < nGroups) {
-                    if (grp + DEPTH - 1 < nGroups) first(grp + DEPTH - 1, vY[(q + DEPTH - 1) % DEPTH], vZ[(q + DEPTH - 1) % DEPTH]);
+#pragma unroll
+                    for (int d = 1; d <= DEPTH; d++)
+                        if (d == hd && grp + d - 1 < nGroups) first(grp + d - 1, vY[(q + d - 1) % DEPTH], vZ[(q + d - 1) % DEPTH]);
                     const int pBase = grp * GSZ;
                     int delivered = 0;
                     long long c0 = tracing ? clock64() : 0;
@@ -283,7 +304,7 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
                         // everything that is missing of every group in flight, oldest first (the youngest group's first loads may
                         // still be on their way: its predicate is evaluated last)
 #pragma unroll
-                        for (int d = 0; d < DEPTH; d++) again(grp + d, vY[(q + d) % DEPTH], vZ[(q + d) % DEPTH]);
+                        for (int d = 0; d < DEPTH; d++) if (d < hd) again(grp + d, vY[(q + d) % DEPTH], vZ[(q + d) % DEPTH]);
                         if (tracing) ph[1] += 1;
                     }
                     if (tracing) { const long long c1 = clock64(); ph[0] += c1 - c0; }
@@ -379,14 +400,8 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
     int tb = tbOf(0);
     using Halo = WaveHalo<OP, FASTDIV, HS>;
     int pDone = 0;                                // steps completed, processing order
-    // the halo of the next HS steps: wait until the halo warp has delivered them, then ring -> registers
-    auto fetchHalo = [&](Halo& h, int t0) {
-        const unsigned need = (unsigned)(pDone + HS);
-        if (ld_acquire_cta_u32(&haloProg) < need) {
-            const long long c0 = tracing ? clock64() : 0;
-            while (ld_acquire_cta_u32(&haloProg) < need) {}
-            if (tracing) ph[1] += clock64() - c0;
-        }
+    // ring -> registers for the HS steps from memory-order step t0
+    auto loadHalo = [&](Halo& h, int t0) {
 #pragma unroll
         for (int s = 0; s < HS; s++) {
             const int p = bwd ? g.nStepsPad - 1 - (t0 + s) : t0 + s;
@@ -395,36 +410,53 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
             if (OP == 0 && FASTDIV) { h.yY[s] = div_refine(h.hy[s]); h.yZ[s] = div_refine(h.hz[s]); }
         }
     };
-    auto halfDone = [&]() {
+    bool haveHalo = false;                        // the halo of the half about to start is in registers already
+    // the halo of this half (wait for the halo warp if it was not prefetched), and -- if it has been delivered already -- the next
+    // half's, whose loads then complete under this half's chain
+    auto halos = [&](Halo& hcur, Halo& hnxt, int t0, int t0next, bool haveNextHalf) {
+        const unsigned prog = ld_acquire_cta_u32(&haloProg);
+        if (!haveHalo) {
+            const unsigned need = (unsigned)(pDone + HS);
+            if (prog < need) {
+                const long long c0 = tracing ? clock64() : 0;
+                while (ld_acquire_cta_u32(&haloProg) < need) {}
+                if (tracing) ph[1] += clock64() - c0;
+            }
+            loadHalo(hcur, t0);
+        }
+        haveHalo = haveNextHalf && prog >= (unsigned)(pDone + 2 * HS);
+        if (haveHalo) loadHalo(hnxt, t0next);
+    };
+    auto halfDone = [&](bool publish) {
         pDone += HS;
-        __syncwarp();
-        if (lane == 0) st_release_cta_u32(&compProg, (unsigned)pDone);
+        if (publish) {          // back-pressure for the halo ring (RH steps deep): once per group is plenty
+            __syncwarp();
+            if (lane == 0) st_release_cta_u32(&compProg, (unsigned)pDone);
+        }
     };
     // first half of group `grp` (operands in `cur`), prefetching the second half of the same slot
-    auto firstHalf = [&](int grp, Ops& cur, Ops& nxt) {
+    auto firstHalf = [&](int grp, Ops& cur, Ops& nxt, Halo& h, Halo& hn) {
         const Slot& S = sm.slot[slot];
         const int s0 = bwd ? HS : 0, sn0 = bwd ? 0 : HS;
         const int t0 = tb + s0;
-        Halo h;
-        fetchHalo(h, t0);
+        halos(h, hn, t0, tb + sn0, true);
         if (t0 >= WTJ + WTK - 2 && t0 + HS - 1 < g.nx)
             wave4_chain<OP, DILU, DOT, false, WIO, FASTDIV, HS, true, NARR, Slot>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad, &S, sn0, &nxt);
         else {
             wave4_chain<OP, DILU, DOT, true, WIO, FASTDIV, HS>(cur, h, out, t0, lane, skew, g.nx, pencil, edgeInY, edgeInZ, hasY, hasZ, last, acc, held, bad);
             wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(S, sn0, lane, nxt);
         }
-        halfDone();
+        halfDone(false);
     };
     // second half of group `grp`; the first half of the next group is prefetched only if its slot has landed already
-    auto secondHalf = [&](int grp, Ops& cur, Ops& nxt) {
+    auto secondHalf = [&](int grp, Ops& cur, Ops& nxt, Halo& h, Halo& hn) {
         const int s0 = bwd ? 0 : HS, sn0 = bwd ? HS : 0;
         const int t0 = tb + s0;
         const bool haveNext = grp + 1 < nGroups;
         const int nslot = slot + 1 == RNG ? 0 : slot + 1;
         const unsigned nparity = slot + 1 == RNG ? parity ^ 1u : parity;
         const Slot& Sn = sm.slot[nslot];
-        Halo h;
-        fetchHalo(h, t0);
+        halos(h, hn, t0, tb + (bwd ? -GSZ : GSZ) + sn0, haveNext);
         const bool pre = haveNext && __all_sync(full, testFull(nslot, nparity));
         const bool interior = t0 >= WTJ + WTK - 2 && t0 + HS - 1 < g.nx;
         if (pre && interior)
@@ -441,10 +473,11 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
                 wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(Sn, sn0, lane, nxt);
             }
         }
-        halfDone();
+        halfDone(true);
         if (lane == 0) arriveEmpty(slot);
         if (grp < 5) stamp(5 + grp);
         if (grp == nGroups - 1) stamp(10);
+        if (a.traceG != nullptr && lane == 0) { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); a.traceG[(size_t)T * nGroups + grp] = t; }
         slot = nslot; parity = nparity;
         tb += bwd ? -GSZ : GSZ;
     };
@@ -452,9 +485,10 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
     const long long cStart = tracing ? clock64() : 0;
     waitFull(0, 0u);
     wave4_fetch<OP, DILU, WIO, FASTDIV, NARR, HS, Slot>(sm.slot[0], bwd ? HS : 0, lane, opsA);
+    Halo haloA, haloB;
     for (int grp = 0; grp < nGroups; grp++) {
-        firstHalf(grp, opsA, opsB);
-        secondHalf(grp, opsB, opsA);
+        firstHalf(grp, opsA, opsB, haloA, haloB);
+        secondHalf(grp, opsB, opsA, haloB, haloA);
     }
     if (DOT) {
         acc = warp_reduce<Sum>(acc);

@@ -419,3 +419,154 @@ def read_case(case_dir, start_dir="0"):
     t_initial, patches = _read_T(case_dir, mesh_patches, start_dir)
     return dict(mesh=mesh, patches=patches, material=_read_material(case_dir), beams=_read_beams(case_dir),
                 controls=_read_controls(case_dir), Tinitial=t_initial, powderZMin=_read_powder(case_dir, mesh))
+
+
+# ------------------------------------------------------------------------------------------------ field files (restart I/O)
+# What additiveFoam writes at a write time and reads back on restart: T and alpha.powder (SOLVER/createFields.H:2-29, AUTO_WRITE;
+# alpha.solid is NO_READ / NO_WRITE and is rebuilt from T, :31-44, :74-78), as [UPSTREAM] volScalarField files in the writeFormat of
+# system/controlDict (`ascii` or `binary`; the tutorials ship `writeFormat binary`).  The internal field is what the resident stepper
+# exchanges; patch `value` entries are written from the caller's patch values where given and as the neighbouring cell otherwise.
+_HEADER = """/*--------------------------------*- C++ -*----------------------------------*\\
+  =========                 |
+  \\\\      /  F ield         | OpenFOAM: The Open Source CFD Toolbox
+   \\\\    /   O peration     | Website:  https://openfoam.org
+    \\\\  /    A nd           | Version:  10
+     \\\\/     M anipulation  |
+\\*---------------------------------------------------------------------------*/
+FoamFile
+{
+    format      %s;
+    class       volScalarField;
+    location    "%s";
+    object      %s;
+}
+// * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * * //
+
+"""
+
+
+def _list_bytes(values, binary, precision):
+    import numpy as np
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    if binary:
+        return b"nonuniform List<scalar> \n%d\n(" % v.size + v.astype("<f8").tobytes() + b")"
+    fmt = "%%.%dg" % precision
+    return ("nonuniform List<scalar> \n%d\n(\n" % v.size + "\n".join(fmt % x for x in v) + "\n)\n").encode()
+
+
+def write_field(case_dir, time_name, name, internal, dimensions, patches, binary=True, precision=8):
+    """Write ``<case>/<time>/<name>`` as OpenFOAM does.  ``patches``: ordered {patch name: dict(type=..., entries...)}; an entry whose
+    value is an array is written as a (nonuniform) List<scalar>, a float as ``uniform``; everything else verbatim."""
+    import numpy as np
+    os.makedirs(os.path.join(case_dir, time_name), exist_ok=True)
+    out = [(_HEADER % ("binary" if binary else "ascii", time_name, name)).encode(),
+           ("dimensions      [%s];\n\n" % " ".join(str(d) for d in dimensions)).encode(), b"internalField   "]
+    internal = np.asarray(internal, dtype=np.float64)
+    if internal.size and np.all(internal == internal.flat[0]):
+        out.append(("uniform %.*g" % (precision if not binary else 17, float(internal.flat[0]))).encode())
+    else:
+        out.append(_list_bytes(internal, binary, precision))
+    out.append(b";\n\nboundaryField\n{\n")
+    for pname, entries in patches.items():
+        out.append(("    %s\n    {\n" % pname).encode())
+        for k, v in entries.items():
+            if isinstance(v, (list, tuple)) or hasattr(v, "dtype"):
+                out.append(("        %-15s " % k).encode() + _list_bytes(v, binary, precision) + b";\n")
+            elif isinstance(v, float):
+                out.append(("        %-15s uniform %.*g;\n" % (k, 17 if binary else precision, v)).encode())
+            else:
+                out.append(("        %-15s %s;\n" % (k, v)).encode())
+        out.append(b"    }\n")
+    out.append(b"}\n\n\n// ************************************************************************* //\n")
+    path = os.path.join(case_dir, time_name, name)
+    with open(path, "wb") as f:
+        f.write(b"".join(out))
+    return path
+
+
+def _read_scalar_entry(data, pos, binary, n_expected=None):
+    """Parse ``uniform x`` or ``nonuniform List<scalar> N ( ... )`` starting at byte offset ``pos`` (after the keyword); returns (value or array, end)."""
+    import numpy as np
+    m = re.compile(rb"\s*(uniform|nonuniform)\s*").match(data, pos)
+    if not m:
+        raise FoamCaseError("field entry is neither uniform nor nonuniform")
+    if m.group(1) == b"uniform":
+        e = data.index(b";", m.end())
+        return float(data[m.end():e].decode()), e + 1
+    m2 = re.compile(rb"List<scalar>\s*(\d+)\s*\(").match(data, m.end())
+    if not m2:
+        raise FoamCaseError("only List<scalar> fields are read")
+    n = int(m2.group(1))
+    if n_expected is not None and n != n_expected:
+        raise FoamCaseError("field has %d values, the mesh %d cells" % (n, n_expected))
+    if binary:
+        raw = data[m2.end():m2.end() + 8 * n]
+        if len(raw) != 8 * n or data[m2.end() + 8 * n:m2.end() + 8 * n + 1] != b")":
+            raise FoamCaseError("truncated binary List<scalar>")
+        return np.frombuffer(raw, dtype="<f8").copy(), data.index(b";", m2.end() + 8 * n) + 1
+    e = data.index(b")", m2.end())
+    vals = np.array(data[m2.end():e].split(), dtype=np.float64)
+    if vals.size != n:
+        raise FoamCaseError("List<scalar> announces %d values and holds %d" % (n, vals.size))
+    return vals, data.index(b";", e) + 1
+
+
+def read_field(path, n_cells=None):
+    """The internal field of a volScalarField file (ascii or binary, uniform or nonuniform) -> numpy array (``n_cells`` values when the
+    field is uniform and ``n_cells`` is given, else the scalar), plus {patch: {key: value}} with ``value`` entries parsed the same way."""
+    import numpy as np
+    data = open(path, "rb").read()
+    head = re.search(rb"FoamFile\s*\{(.*?)\}", data, re.S)
+    if not head:
+        raise FoamCaseError("%s: no FoamFile header" % path)
+    binary = re.search(rb"format\s+binary\s*;", head.group(1)) is not None
+    if not re.search(rb"class\s+volScalarField\s*;", head.group(1)):
+        raise FoamCaseError("%s: not a volScalarField" % path)
+    m = re.compile(rb"internalField").search(data, head.end())
+    if not m:
+        raise FoamCaseError("%s: no internalField" % path)
+    internal, pos = _read_scalar_entry(data, m.end(), binary, n_cells if n_cells else None)
+    if np.isscalar(internal) and n_cells:
+        internal = np.full(n_cells, internal)
+    patches = {}
+    b = re.compile(rb"boundaryField\s*\{").search(data, pos)
+    pos = b.end() if b else len(data)
+    pat = re.compile(rb"\s*([A-Za-z_][\w.]*)\s*\{")
+    while b:
+        pm = pat.match(data, pos)
+        if not pm:
+            break
+        pos = pm.end()
+        entries = {}
+        while True:
+            km = re.compile(rb"\s*(\}|[A-Za-z_]\w*)").match(data, pos)
+            if not km:
+                raise FoamCaseError("%s: malformed patch %s" % (path, pm.group(1).decode()))
+            pos = km.end()
+            if km.group(1) == b"}":
+                break
+            key = km.group(1).decode()
+            if re.compile(rb"\s*(uniform|nonuniform)\b").match(data, pos):
+                entries[key], pos = _read_scalar_entry(data, pos, binary)
+            else:
+                e = data.index(b";", pos)
+                entries[key] = data[pos:e].decode().strip()
+                pos = e + 1
+        patches[pm.group(1).decode()] = entries
+    return internal, patches
+
+
+def write_time_directory(case_dir, time_name, case, T, alpha_powder, binary=True, precision=8):
+    """What `runTime.write()` leaves for a restart: ``<time>/T`` with the boundary types of the case, and ``<time>/alpha.powder``."""
+    names = case.get("patchNames") or ["patch%d" % i for i in range(len(case["patches"]))]
+    tp, ap = {}, {}
+    for name, p in zip(names, case["patches"]):
+        if p["type"] == abi.BC_FIXED_VALUE:
+            tp[name] = dict(type="fixedValue", value=float(p["value"]))
+        elif p["type"] == abi.BC_MIXED_TEMPERATURE:
+            tp[name] = dict(type="mixedTemperature", h=repr(float(p["h"])), emissivity=repr(float(p["emissivity"])), Tinf=float(p["Tinf"]))
+        else:
+            tp[name] = dict(type="zeroGradient")
+        ap[name] = dict(type="zeroGradient")
+    return (write_field(case_dir, time_name, "T", T, [0, 0, 0, 1, 0, 0, 0], tp, binary, precision),
+            write_field(case_dir, time_name, "alpha.powder", alpha_powder, [0, 0, 0, 0, 0, 0, 0], ap, binary, precision))

@@ -29,7 +29,7 @@ SYMBOLS = [
     "b200_profile_name", "b200_profile_read", "b200_ldu_create", "b200_ldu_destroy", "b200_ldu_set_block", "b200_ldu_solve",
     "b200_ldu_solve_dev", "b200_ldu_amul", "b200_ldu_amul_dev", "b200_ldu_precondition", "b200_ldu_levels",
     "b200_beam_qdot", "b200_beam_qdot_sub", "b200_beam_shape_v0", "b200_beam_shape_weight", "b200_beam_absorption_eta", "b200_mixed_temperature_value_fraction", "b200_case_create", "b200_case_destroy", "b200_case_running", "b200_case_step",
-    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_set_field_async", "b200_case_apply_staged",
+    "b200_case_n_cells", "b200_case_get_field", "b200_case_set_field", "b200_case_reset_alpha_solid", "b200_case_set_field_async", "b200_case_apply_staged",
     "b200_case_get_field_async", "b200_case_transfers_wait", "b200_case_melt_pool_dimensions", "b200_case_isotherm_depth", "b200_case_sources_update", "b200_case_solidification_enable",
     "b200_case_solidification_events", "b200_selftest_division", "b200_case_kernel_launches",
     "b200_scan_path_parse", "b200_create_scan_path",
@@ -364,6 +364,18 @@ class Case:
         a = _f64(a)
         assert a.size == self.n_local
         _check(self.L.b200_case_set_field(self.h, f, _P(a)))
+
+    def reset_alpha_solid(self):
+        """Restart: alpha.solid (and its old-time level) rebuilt from T through the thermoPath table, properties updated (createFields.H:31-44,74-78,112)."""
+        _check(self.L.b200_case_reset_alpha_solid(self.h))
+
+    def restart(self, T, alpha_powder=None):
+        """Continue from fields of a time directory (foamcase.read_field): T and alpha.powder as read, alpha.solid rebuilt from T -- what
+        the reference does when started from a written time (createFields.H:2-44,74-78)."""
+        if alpha_powder is not None:
+            self.set_field(abi.FIELD_ALPHA_POWDER, alpha_powder)
+        self.set_field(abi.FIELD_T, T)
+        self.reset_alpha_solid()
 
     def field_into(self, f, out):
         """get_field into an existing (e.g. pinned) array."""

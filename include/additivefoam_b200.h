@@ -279,6 +279,10 @@ int  b200_case_step(b200_case* c, b200_step_report* report);
 int  b200_case_n_cells(b200_case* c, int64_t* nLocal, int64_t* nGlobal);
 int  b200_case_get_field(b200_case* c, int32_t field, double* out);
 int  b200_case_set_field(b200_case* c, int32_t field, const double* in);
+/* Restart (SOLVER/createFields.H:31-44,74-78): alpha.solid is never written or read by the reference -- after T has been set from a
+ * time directory it is rebuilt as min(max(interpolateXY(T, thermoPath), 0), 1), its old-time level with it, and the properties are
+ * updated (createFields.H:112). */
+int  b200_case_reset_alpha_solid(b200_case* c);
 /* Streamed host I/O for an application that feeds the step and consumes its result without waiting on either (e.g. a solver
  * application whose function objects read T every step in their `execute()`).  Host buffers must be pinned.
  *   set_field_async : host -> a device staging buffer on a copy stream of its own; returns at once.
@@ -328,7 +332,7 @@ int  b200_selftest_division(b200_ctx* ctx, int64_t nPairs, int64_t seed, int32_t
 int  b200_case_kernel_launches(b200_case* c, int64_t* launches);
 
 /* Scan path text -> nSegments x 6 table (MHS/movingBeam/movingBeam.C:89-148: header line
- * skipped, blank lines skipped).  Returns the number of segments, or -1. */
+ * skipped, blank lines skipped).  Returns the number of segments, or -1 if they do not fit; out == NULL only counts. */
 int  b200_scan_path_parse(const char* text, double* out, int32_t maxSegments);
 
 /* Raster scan path of one rotation angle as file text -- what applications/utilities/createScanPath writes into

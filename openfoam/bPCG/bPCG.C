@@ -50,11 +50,14 @@ b200_ctx* Foam::b200SolverBase::ctx()
             Pstream::scatter(idList);
             forAll(idList, i) { id[i] = idList[i]; }
         }
+        // the ranks of a node share its GPUs round-robin (one rank per GPU when there are as many)
+        int nDevices = 1;
+        b200Check(b200_device_count(&nDevices), "b200_device_count");
         b200Check
         (
             b200_ctx_create
             (
-                Pstream::parRun() ? Pstream::myProcNo() % 8 : 0,
+                Pstream::parRun() ? Pstream::myProcNo() % nDevices : 0,
                 Pstream::parRun() ? id : nullptr,
                 Pstream::parRun() ? Pstream::myProcNo() : 0,
                 Pstream::parRun() ? Pstream::nProcs() : 1,
@@ -69,13 +72,26 @@ b200_ctx* Foam::b200SolverBase::ctx()
 
 b200_ldu* Foam::b200SolverBase::handle() const
 {
-    // addressing is cached per lduAddressing object; coefficients are fresh per solve
-    static std::map<const lduAddressing*, b200_ldu*> cache;
+    // addressing is cached per lduAddressing object; coefficients are fresh per solve.  The entry is validated before reuse
+    // (sizes and the address arrays themselves): a mesh that was destroyed or changed topology can leave another lduAddressing
+    // at the same address.
+    struct Cached { b200_ldu* h; label nCells, nFaces; const label* lower; const label* upper; };
+    static std::map<const lduAddressing*, Cached> cache;
     const lduAddressing& addr = matrix_.lduAddr();
     auto it = cache.find(&addr);
     if (it != cache.end())
     {
-        return it->second;
+        const Cached& c = it->second;
+        if
+        (
+            c.nCells == addr.size() && c.nFaces == addr.lowerAddr().size()
+         && c.lower == addr.lowerAddr().begin() && c.upper == addr.upperAddr().begin()
+        )
+        {
+            return c.h;
+        }
+        b200_ldu_destroy(c.h);
+        cache.erase(it);
     }
 
     DynamicList<label> neighbRank, size;
@@ -111,16 +127,45 @@ b200_ldu* Foam::b200SolverBase::handle() const
         ),
         "b200_ldu_create"
     );
-    // optional: `blockNx/blockNy/blockNz` in the solver dictionary declares a single blockMesh hex block (serial runs); the
-    // library verifies the addressing bit-exactly and switches to its addressing-free kernels
-    const label bnx = controlDict_.lookupOrDefault<label>("blockNx", 0);
-    const label bny = controlDict_.lookupOrDefault<label>("blockNy", 0);
-    const label bnz = controlDict_.lookupOrDefault<label>("blockNz", 0);
-    if (bnx > 0 && bny > 0 && bnz > 0 && !Pstream::parRun())
+
+    // The addressing-free block kernels.  `blockNx/blockNy/blockNz` in the solver dictionary declare this rank's cells to be one
+    // blockMesh hex block (an error if the addressing says otherwise).  Without them (`blockDetect yes`, the default) the shape is
+    // read off the faces cell 0 owns -- in blockMesh cell order they lead to cells 1, nx and nx*ny -- and offered to the library,
+    // which compares the closed form with the whole addressing bit for bit and keeps the general kernels if it differs.  That also
+    // covers each rank of a `simple` / `hierarchical` decomposition of a block: its interior is a block, the processor patches stay
+    // coupled interfaces.
+    label bnx = controlDict_.lookupOrDefault<label>("blockNx", 0);
+    label bny = controlDict_.lookupOrDefault<label>("blockNy", 0);
+    label bnz = controlDict_.lookupOrDefault<label>("blockNz", 0);
+    const bool declared = bnx > 0 && bny > 0 && bnz > 0;
+    if (!declared && controlDict_.lookupOrDefault<Switch>("blockDetect", true) && addr.size() > 0)
     {
-        b200Check(b200_ldu_set_block(h, bnx, bny, bnz), "b200_ldu_set_block");
+        const labelUList& l = addr.lowerAddr();
+        const labelUList& u = addr.upperAddr();
+        label owned = 0;
+        while (owned < l.size() && owned < 3 && l[owned] == 0) owned++;
+        const label nCells = addr.size();
+        bnx = owned >= 2 ? u[1] : (owned == 1 ? nCells : 1);
+        const label nxny = owned >= 3 ? u[2] : nCells;
+        if (bnx > 0 && nxny % bnx == 0 && nCells % nxny == 0)
+        {
+            bny = nxny/bnx;
+            bnz = nCells/nxny;
+        }
+        else
+        {
+            bnx = bny = bnz = 0;
+        }
     }
-    cache[&addr] = h;
+    if (bnx > 0 && bny > 0 && bnz > 0)
+    {
+        const int rc = b200_ldu_set_block(h, bnx, bny, bnz);
+        if (rc != 0 && declared)
+        {
+            b200Check(rc, "b200_ldu_set_block");
+        }
+    }
+    cache[&addr] = Cached{h, addr.size(), addr.lowerAddr().size(), addr.lowerAddr().begin(), addr.upperAddr().begin()};
     return h;
 }
 

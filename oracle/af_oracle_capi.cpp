@@ -235,6 +235,18 @@ int afo_case_set_field(void* h, int f, const scalar* in)
     }
     return 0;
 }
+// Restart (createFields.H:31-44,74-78,112): alpha.solid and its old-time level from T through the thermoPath table, then updateProperties
+int afo_case_reset_alpha_solid(void* h)
+{
+    Case* c = (Case*)h;
+    for (RankState& s : c->rk)
+        for (label i = 0; i < s.mesh.nCells(); i++) {
+            s.alpha1[i] = std::min(std::max(interpolateXY(s.T[i], c->thermoX, c->thermoY), 0.0), 1.0);
+            s.alpha1old[i] = s.alpha1[i];
+        }
+    c->updateProperties();
+    return 0;
+}
 int afo_case_residual_log(void* h, scalar* out, label maxLog)
 {
     Case* c = (Case*)h;

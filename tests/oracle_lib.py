@@ -41,6 +41,7 @@ def load():
     L.afo_case_isotherm_depth.argtypes = [C.c_void_p, C.c_int, dp, dp]
     L.afo_case_sources_probe.argtypes = [C.c_void_p, C.c_double, dp]
     L.afo_case_pre_step_state.argtypes = [C.c_void_p, dp]
+    L.afo_case_reset_alpha_solid.argtypes = [C.c_void_p]
     L.afo_case_n_patches.argtypes = [C.c_void_p]
     L.afo_case_patch_size.restype = C.c_int64
     L.afo_case_patch_size.argtypes = [C.c_void_p, C.c_int]
@@ -107,6 +108,15 @@ class OracleCase:
     def set_field(self, f, a):
         a = np.ascontiguousarray(a, dtype=np.float64)
         assert self.L.afo_case_set_field(self.h, f, P(a)) == 0
+
+    def restart(self, T, alpha_powder=None):
+        if alpha_powder is not None:
+            self.set_field(abi.FIELD_ALPHA_POWDER, alpha_powder)
+        self.set_field(abi.FIELD_T, T)
+        self.reset_alpha_solid()
+
+    def reset_alpha_solid(self):
+        assert self.L.afo_case_reset_alpha_solid(self.h) == 0
 
     def pre_step_state(self):
         """updateProperties() (so that kappa, Cp are what the next step's controls see) and T.oldTime()."""

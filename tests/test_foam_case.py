@@ -248,3 +248,98 @@ def test_case_read_from_a_directory_runs_like_the_oracle(ctx, oracle, tmp_path):
     assert float(np.max(np.abs(g.field(abi.FIELD_ALPHA_SOLID) - o.field(abi.FIELD_ALPHA_SOLID)))) < 1e-9
     assert g.field(abi.FIELD_T).max() > 1000.0
     g.close(); o.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# restart I/O: the time directory additiveFoam writes and reads back -- T and alpha.powder as [UPSTREAM]
+# volScalarField files, ascii or binary (createFields.H:2-29; controlDict writeFormat); alpha.solid is rebuilt from T (:31-44,74-78)
+def test_field_files_round_trip_in_both_write_formats(tmp_path):
+    from additivefoam_b200 import foamcase
+    case = cases.amb2018_02_b(n=(7, 5, 3))
+    rng = np.random.default_rng(5)
+    T = rng.uniform(300.0, 3200.0, 105)
+    powder = (rng.uniform(0, 1, 105) > 0.6).astype(np.float64)
+    for binary in (True, False):
+        pT, pA = foamcase.write_time_directory(str(tmp_path), "0.0005", case, T, powder, binary=binary, precision=17)
+        head = open(pT, "rb").read(700).decode(errors="replace")
+        assert "class       volScalarField;" in head and ("format      binary;" if binary else "format      ascii;") in head
+        gotT, patches = foamcase.read_field(pT, 105)
+        gotA, _ = foamcase.read_field(pA, 105)
+        assert np.array_equal(gotT, T) and np.array_equal(gotA, powder)
+        assert [p["type"] for p in patches.values()] == ["zeroGradient", "mixedTemperature", "zeroGradient"]
+        assert patches["patch1"]["Tinf"] == 300.0 and float(patches["patch1"]["h"]) == 10.0
+    # default ascii precision is the case's writePrecision: values come back to 8 significant digits
+    pT, _ = foamcase.write_time_directory(str(tmp_path), "0.001", case, T, powder, binary=False, precision=8)
+    assert np.allclose(foamcase.read_field(pT, 105)[0], T, rtol=1e-7, atol=0)
+    # a uniform field is written as `uniform`, and read back at the mesh size
+    pT, _ = foamcase.write_time_directory(str(tmp_path), "0", case, np.full(105, 300.0), np.zeros(105))
+    assert b"internalField   uniform 300;" in open(pT, "rb").read()
+    assert np.array_equal(foamcase.read_field(pT, 105)[0], np.full(105, 300.0))
+    with pytest.raises(foamcase.FoamCaseError):
+        foamcase.read_field(_truncate(tmp_path), 24)
+
+
+def _truncate(tmp_path):
+    """A binary field file cut short: must be refused, not zero-filled."""
+    from additivefoam_b200 import foamcase
+    case = cases.amb2018_02_b(n=(4, 3, 2))
+    p, _ = foamcase.write_time_directory(str(tmp_path), "9", case, np.arange(24.0) + 1.5, np.zeros(24), binary=True)
+    data = open(p, "rb").read()
+    i = data.index(b"List<scalar>")
+    open(p, "wb").write(data[:i + 60])
+    return p
+
+
+def test_restart_rebuilds_alpha_solid_from_temperature(oracle):
+    """Oracle side of the restart: stop after 12 steps, write the time directory, start a fresh case from it (alpha.solid from T through
+    the thermoPath table, createFields.H:74-78) and continue -- the continued run must equal the uninterrupted one in T; alpha.solid
+    differs from the run's own only where the solidification history made it differ from the equilibrium table (it is not a file)."""
+    import tempfile
+    import oracle_lib as ol
+    case = cases.amb2018_02_b(n=(40, 10, 6), explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC, writeInterval=0.0)
+    a = ol.OracleCase(case, lib=oracle)
+    for _ in range(12):
+        ra = a.step()
+    with tempfile.TemporaryDirectory() as d:
+        pT, pA = foamcase.write_time_directory(d, "%g" % ra.time, case, a.field(abi.FIELD_T), a.field(abi.FIELD_ALPHA_POWDER), binary=True)
+        T0, _ = foamcase.read_field(pT, a.n)
+        P0, _ = foamcase.read_field(pA, a.n)
+    assert np.array_equal(T0, a.field(abi.FIELD_T))
+    b = ol.OracleCase(case, lib=oracle)
+    b.restart(T0, P0)
+    alpha = b.field(abi.FIELD_ALPHA_SOLID)
+    assert alpha.min() >= 0.0 and alpha.max() <= 1.0
+    table = np.clip(np.interp(T0, case["material"]["thermoT"], case["material"]["thermoAlpha"]), 0.0, 1.0)
+    assert np.allclose(alpha, table, rtol=0, atol=1e-14)
+    assert np.array_equal(b.field(abi.FIELD_T_OLD), T0)
+
+
+@pytest.mark.gpu
+def test_gpu_restart_from_a_written_time_directory(ctx, oracle, tmp_path):
+    """GPU side: a run is stopped in the mushy-zone phase, its time directory written in the tutorials' binary writeFormat, read back,
+    and a fresh resident case restarted from it (b200_case_set_field + b200_case_reset_alpha_solid); the oracle does the same.  The
+    rebuilt alpha.solid is bit-equal (pure table arithmetic), and six further steps stay within the north-star bound."""
+    import oracle_lib as ol
+    from additivefoam_b200 import lib
+    case = cases.amb2018_02_b(n=(60, 12, 8), explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC, writeInterval=0.0)
+    g = lib.Case(ctx, case)
+    for _ in range(30):
+        rep = g.step()
+    T = g.field(abi.FIELD_T)
+    assert T.max() > 1410.0
+    pT, pA = foamcase.write_time_directory(str(tmp_path), "%g" % rep.time, case, T, g.field(abi.FIELD_ALPHA_POWDER), binary=True)
+    g.close()
+    T0, _ = foamcase.read_field(pT, T.size)
+    P0, _ = foamcase.read_field(pA, T.size)
+    assert np.array_equal(T0, T)
+    g2, o2 = lib.Case(ctx, case), ol.OracleCase(case, lib=oracle)
+    g2.restart(T0, P0); o2.restart(T0, P0)
+    assert np.array_equal(g2.field(abi.FIELD_ALPHA_SOLID), o2.field(abi.FIELD_ALPHA_SOLID))
+    assert np.array_equal(g2.field(abi.FIELD_KAPPA), o2.field(abi.FIELD_KAPPA))
+    for s in range(6):
+        rg, ro = g2.step(), o2.step()
+        assert rg.nThermoCorr == ro.nThermoCorr and abs(rg.lastSolveIterations - ro.lastSolveIterations) <= 1
+        eT = float(np.max(np.abs(g2.field(abi.FIELD_T) - o2.field(abi.FIELD_T))) / np.max(np.abs(o2.field(abi.FIELD_T))))
+        eA = float(np.max(np.abs(g2.field(abi.FIELD_ALPHA_SOLID) - o2.field(abi.FIELD_ALPHA_SOLID))))
+        assert eT < 1e-9 and eA < 1e-9, (s, eT, eA)
+    g2.close(); o2.close()
