@@ -441,8 +441,10 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     // bandwidth does (thousands of tiles)
     const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : std::string(e) == "multi" ? 3 : std::string(e) == "tri" ? 4 : 2; }();
     const bool oneWarp = forced == 1;
-    const bool tri = forced == 4;
-    const bool multi = forced == 3 || (forced == 0 && a.g.nTiles <= 1536);
+    // default: where the dependency chain across tiles bounds the sweep (few tiles: thin slabs, small blocks) the three-role kernel
+    // k_wave4, whose tiles follow their producers at a third less lag; where bandwidth does (thousands of tiles) k_wave2
+    const bool tri = forced == 4 || (forced == 0 && a.g.nTiles <= 1536);
+    const bool multi = forced == 3;
     if (op == 0 && !oneWarp) {      // the warp-specialised factor sweep streams the diagonal from wave order as well
         k_wave_from_natural<<<waveVecGrid(), 256, 0, s>>>(a.g, rA, wave[13], 1.0, d_state); B200_LAUNCH_CHECK();
     }

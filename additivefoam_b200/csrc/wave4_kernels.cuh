@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
                         }
                         if (k > delivered) {
                             // back-pressure: the ring entries about to be overwritten have been consumed (never waits in practice)
-                            while ((int)ld_acquire_cta_u32(&compProg) + RH < pBase + k) {}
+                            while ((int)ld_acquire_cta_u32(&compProg) + RH < pBase + k) __nanosleep(200);      // (a tight spin on shared memory slows the compute warp's LDS / SHFL)
                             if (lane < NEY && pY >= delivered && pY < k) hyRing[((pBase + pY) & (RH - 1)) * WTK + tkY] = vY[q];
 #pragma unroll
                             for (int r = 0; r < NZ; r++) {

@@ -35,12 +35,20 @@ def gather(part, sizes):
 ok, lines = True, []
 problems = [("chain+random 3000", 3000, helpers.random_ldu_addressing(3000, 7000, 31), False),
             ("chain+random 20000 asym", 20000, helpers.random_ldu_addressing(20000, 50000, 32), True),
-            ("block 24x10x9", 24 * 10 * 9, helpers.block_addressing_np((24, 10, 9)), False)]
+            ("block 24x10x9", 24 * 10 * 9, helpers.block_addressing_np((24, 10, 9)), False),
+            # a block cut into whole z-layers: every rank's share is itself a block (what `simple (1 1 N)` gives bPCG); the block
+            # kernels then do the interior and the processor interfaces stay coupled
+            ("per-rank blocks 24x10x%d" % (4 * world), 24 * 10 * 4 * world, helpers.block_addressing_np((24, 10, 4 * world)), False),
+            ("per-rank blocks 16x12x%d asym" % (3 * world), 16 * 12 * 3 * world, helpers.block_addressing_np((16, 12, 3 * world)), True)]
 for name, n, (lo, up), asym in problems:
     diag, upper, lower, x, b = helpers.spd_coefficients(n, lo, up, seed=77, asym=asym)
     d = partition.decompose_ldu(n, lo, up, diag, upper, lower, rank, world)
     sizes = [n * (r + 1) // world - n * r // world for r in range(world)]
-    s = lib.LduSolver(ctx, d["lower"], d["upper"], d["n"], interfaces=d["interfaces"])
+    blk = None
+    if name.startswith("per-rank blocks"):
+        nx_, ny_ = (24, 10) if not asym else (16, 12)
+        blk = (nx_, ny_, d["n"] // (nx_ * ny_))
+    s = lib.LduSolver(ctx, d["lower"], d["upper"], d["n"], interfaces=d["interfaces"], block=blk)
     xs, bs = x[d["c0"]:d["c1"]], b[d["c0"]:d["c1"]]
     y = gather(s.amul(xs, d["diag"], d["upper_coeffs"], d["lower_coeffs"], bou_coeffs=d["bou_coeffs"]), sizes)
     results = {}

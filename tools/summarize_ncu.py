@@ -1,11 +1,19 @@
-"""Turn the ncu outputs of one bench.py command into the committed summaries under profiles/.
-Usage: python tools/summarize_ncu.py <cells> <launches.csv> <full.ncu-rep> [more.ncu-rep ...]"""
+"""Turn the ncu outputs of one bench.py command into the committed summaries under profiles/ and into profiles/r2_traffic.json,
+the per-launch DRAM bytes bench.py reports as `roofline.traffic` -- keyed by the hash of the CUDA sources, so that a number taken on
+another build is never reported.
+Usage: python tools/summarize_ncu.py <cells per GPU> <launches.csv> <full.ncu-rep> [more.ncu-rep ...]     (prefix: env PREFIX, default r2)"""
 import collections
 import csv
 import subprocess
 import sys
 
+import json
+import os
+
 cells, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
+PREFIX = os.environ.get("PREFIX", "r2")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 rows = [r for r in csv.reader(open(launches)) if r and not r[0].startswith("==")]
@@ -21,7 +29,7 @@ for r in rows[1:]:
     agg[name][0] += 1
     agg[name][1] += v
 tot = sum(v[1] for v in agg.values())
-with open(f"profiles/r1_launch_list_summary_{cells}.csv", "w") as f:
+with open(f"profiles/{PREFIX}_launch_list_summary_{cells}.csv", "w") as f:
     f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none over `python bench.py --steps 2 --warmup 3 --no-cpu-baseline "
             f"--no-e2e` ({cells} cells per GPU); cold-cache, serialised: compare SHARES with bench.py's live shares\n")
     f.write(f"# launches captured: {sum(v[0] for v in agg.values())}\nkernel,launches,total_ms,share\n")
@@ -30,7 +38,8 @@ with open(f"profiles/r1_launch_list_summary_{cells}.csv", "w") as f:
 
 want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__grid_size", "launch__block_size"]
-with open(f"profiles/r1_top_kernels_ncu_full_{cells}.csv", "w") as f:
+traffic_rows = []
+with open(f"profiles/{PREFIX}_top_kernels_ncu_full_{cells}.csv", "w") as f:
     w = csv.writer(f)
     w.writerow(["kernel", "duration_ms", "dram_read_bytes", "dram_write_bytes", "dram_throughput_pct_of_peak", "registers_per_thread",
                 "warps_active_pct", "grid", "block"])
@@ -44,5 +53,37 @@ with open(f"profiles/r1_top_kernels_ncu_full_{cells}.csv", "w") as f:
             for m in want:
                 v = float(r[col[m]].replace(",", ""))
                 vals.append(v * UNIT.get(units[col[m]], 1.0))
-            w.writerow([r[col["Kernel Name"]].split("(")[0].replace("void ", "")] + [f"{v:.6g}" for v in vals])
-print(open(f"profiles/r1_top_kernels_ncu_full_{cells}.csv").read())
+            kname = r[col["Kernel Name"]].split("(")[0].replace("void ", "")
+            w.writerow([kname] + [f"{v:.6g}" for v in vals])
+            traffic_rows.append((kname, vals[1] + vals[2]))
+print(open(f"profiles/{PREFIX}_top_kernels_ncu_full_{cells}.csv").read())
+
+# ---- per-launch DRAM traffic of the kernels bench.py's roofline can name, for THIS build
+def group_of(k):
+    for pat, g in (("k_wave2<(int)2", "sweep_bwd"), ("k_wave4<(int)2", "sweep_bwd"), ("k_wave3<(int)2", "sweep_bwd"), ("k_wave2<(int)1", "sweep_fwd"),
+                   ("k_wave4<(int)1", "sweep_fwd"), ("k_wave3<(int)1", "sweep_fwd"), ("k_wave2<(int)0", "factor"), ("k_wave4<(int)0", "factor"),
+                   ("k_amul_block", "amul"), ("k_corrector", "corrector"), ("k_assemble_implicit", "assemble"), ("k_props", "props"),
+                   ("k_dinum", "dinum"), ("k_faces", "faces"), ("k_alpha_update", "alpha"), ("k_normfactor_block", "normfactor")):
+        if pat in k:
+            return g
+    return None
+
+
+import bench  # noqa: E402  (source_hash)
+per = collections.defaultdict(list)
+for k, b in traffic_rows:
+    g = group_of(k)
+    if g and b > 1e6:                       # the instantiations that return at once (exact factor sweep) move nothing
+        per[g].append(b)
+path = os.path.join(ROOT, "profiles", f"{PREFIX}_traffic.json")
+data = {"source_hash": bench.source_hash(), "bytes_per_launch": {}}
+if os.path.exists(path):
+    try:
+        old = json.load(open(path))
+        if old.get("source_hash") == data["source_hash"]:
+            data = old
+    except Exception:
+        pass
+data["bytes_per_launch"][str(cells)] = {g: sum(v) / len(v) for g, v in per.items()}
+json.dump(data, open(path, "w"), indent=1)
+print(open(path).read())
