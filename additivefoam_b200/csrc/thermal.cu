@@ -136,7 +136,13 @@ ThermalCase::ThermalCase(Ctx* c, const b200_case_desc& desc) : ctx(c)
         const double cz = geo.oz + (k + geo.k0 + 0.5) * geo.dz;
         if (cz > desc.powderZMin) { k_fill<<<flat_grid(ctx, (int64_t)plane), BLK, 0, s>>>((int64_t)plane, alpha3 + (size_t)k * plane, 1.0); B200_LAUNCH_CHECK(); }
     }
-    time_ = ctl.startTime; deltaT_ = ctl.deltaT;
+    time_ = ctl.startTime; deltaT_ = ctl.deltaT; deltaT0_ = deltaT_; deltaTSave_ = deltaT_;
+    B200_CHECK(ctl.ddtScheme == B200_DDT_EULER || ctl.ddtScheme == B200_DDT_BACKWARD, "ddtScheme: Euler and backward are implemented (CrankNicolson is not)");
+    if (backward()) {
+        Toldold = allocField(); alpha1oldold = allocField();
+        k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, Toldold, Tinitial); B200_LAUNCH_CHECK();
+        k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, alpha1oldold, a0); B200_LAUNCH_CHECK();
+    }
     for (int b = 0; b < desc.nBeams; b++) sources.emplace_back(desc.beams[b], time_, ctl.endTime);
 
     ldu.reset(new Ldu(ctx, dims));
@@ -146,7 +152,7 @@ ThermalCase::ThermalCase(Ctx* c, const b200_case_desc& desc) : ctx(c)
     if (rankAbove >= 0) bouPtrs[nb++] = sides[B200_ZMAX].bouCoeff;
 
     double a, b2, c2;
-    updatePropertiesAndNumbers(a, b2, c2);            // createFields.H:112
+    updatePropertiesAndNumbers(a, b2, c2, true);      // createFields.H:112
     ctx->sync();
 }
 
@@ -179,6 +185,8 @@ double* ThermalCase::field(int f)
     case B200_FIELD_T0: return T0;
     case B200_FIELD_T_OLD: return Told;
     case B200_FIELD_ALPHA_SOLID_OLD: return alpha1old;
+    case B200_FIELD_T_OLD_OLD: B200_CHECK(Toldold != nullptr, "the second old-time level exists only with ddtScheme backward"); return Toldold;
+    case B200_FIELD_ALPHA_SOLID_OLD_OLD: B200_CHECK(alpha1oldold != nullptr, "the second old-time level exists only with ddtScheme backward"); return alpha1oldold;
     }
     throw Error("unknown field id");
 }
@@ -211,7 +219,7 @@ void ThermalCase::resetAlphaSolidFromT()
     k_alpha_from_T<<<flat_grid(ctx, n), BLK, 2 * (size_t)mat.nThermo * sizeof(double), ctx->stream>>>(n, T, d_thermo, mat.nThermo, alpha1, alpha1old);
     B200_LAUNCH_CHECK();
     double a, b2, c2;
-    updatePropertiesAndNumbers(a, b2, c2);            // createFields.H:112 #include "updateProperties.H"
+    updatePropertiesAndNumbers(a, b2, c2, true);      // createFields.H:112 #include "updateProperties.H"
     ctx->sync();
 }
 
@@ -373,15 +381,44 @@ void ThermalCase::readReductions(int n)
     ctx->sync();
 }
 
+BackwardCoeffs ThermalCase::backwardCoeffs(int nOld) const
+{
+    const double dt0 = nOld < 2 ? 1.0e15 : deltaT0_;            // backwardDdtScheme::deltaT0_(vf): great while vf.nOldTimes() < 2
+    BackwardCoeffs k;
+    k.rDeltaT = 1.0 / deltaT_;
+    k.coefft = 1 + deltaT_ / (deltaT_ + dt0);
+    k.coefft00 = deltaT_ * deltaT_ / (dt0 * (deltaT_ + dt0));
+    k.coefft0 = k.coefft + k.coefft00;
+    k.on = true;
+    return k;
+}
+
+// [UPSTREAM] GeometricField::oldTime(): a level that does not exist yet is created as a copy of the level above it
+void ThermalCase::touchOldTimes(bool ofT, int levels)
+{
+    int& nOld = ofT ? TnOld : a1nOld;
+    if (nOld < 2 && levels >= 2) {
+        const size_t n = (size_t)dims.nCells();
+        B200_CUDA(cudaMemcpyAsync(ofT ? Toldold : alpha1oldold, ofT ? Told : alpha1old, n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    nOld = std::max(nOld, levels);
+}
+
 // updateProperties.H + the two numbers of setDeltaT.H (alphaCoNum without dt history issues, DiNum/dt)
-void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1)
+void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1, bool propertiesOnly)
 {
     cudaStream_t s = ctx->stream;
     MatDev m;
     std::memcpy(m.kappa, mat.kappa, sizeof(m.kappa)); std::memcpy(m.Cp, mat.Cp, sizeof(m.Cp));
     m.rho = mat.rho; m.Lf = mat.Lf; m.Tliq = Tliq; m.Tsol = Tsol;
+    // setDeltaT.H:6-11 evaluates fvc::ddt(T) with the scheme of fvSchemes (only when adjustTimeStep: the levels are created there)
+    BackwardCoeffs kb{1.0 / deltaT_, 1, 1, 0, false};
+    if (!propertiesOnly) {             // (createFields.H:112 runs updateProperties.H alone: no fvc::ddt(T), no old-time level is created)
+        if (backward() && ctl.adjustTimeStep) { kb = backwardCoeffs(TnOld); touchOldTimes(true, 2); }
+        else if (ctl.adjustTimeStep) touchOldTimes(true, 1);
+    }
     { ProfScope ps_(ctx, PC_PROPS);
-    k_props<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, m, T, Told, alpha1, alpha3, kappa, rKappa, Cp, 1.0 / deltaT_, deltaT_, red);
+    k_props<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, m, T, Told, alpha1, alpha3, kappa, rKappa, Cp, 1.0 / deltaT_, deltaT_, red, kb, Toldold);
     B200_LAUNCH_CHECK(); }
     haloExchange(kappa);
     haloExchange(rKappa);
@@ -564,8 +601,13 @@ void ThermalCase::assembleBase(bool explicitSolve, double rDeltaT)
             B200_LAUNCH_CHECK();
         }
         { ProfScope ps_(ctx, PC_FACES); k_faces<false><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
-        { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho); B200_LAUNCH_CHECK(); }
+        // thermoScheme.H:34-39 fvm::ddt(T) with the scheme of fvSchemes
+        BackwardCoeffs kT{rDeltaT, 1, 1, 0, false};
+        if (backward()) kT = backwardCoeffs(TnOld);
+        touchOldTimes(true, backward() ? 2 : 1);
+        { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho, kT, Toldold); B200_LAUNCH_CHECK(); }
     } else {
+        touchOldTimes(true, 1);            // thermoScheme.H:25-31: the explicit form always uses EulerDdtScheme
         haloExchange(T);
         { ProfScope ps_(ctx, PC_FACES); k_faces<true><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
         { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_explicit<<<grid, BLK, 0, s>>>(dims, geo, sidesDev, Cp, Told, T, qDot, upper, rKappa, diag0, source0, rDeltaT, mat.rho);
@@ -584,8 +626,12 @@ void ThermalCase::step(b200_step_report* rep)
     updateSources();                                                   // :74
     // runTime++ (:76)
     { ProfScope ps_(ctx, PC_COPY);
+    // [UPSTREAM] GeometricField::storeOldTimes: the levels that exist shift (the second one by swapping buffers: its old content is dead)
+    if (TnOld >= 2) std::swap(Told, Toldold);
+    if (a1nOld >= 2) std::swap(alpha1old, alpha1oldold);
     B200_CUDA(cudaMemcpyAsync(Told, T, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
     B200_CUDA(cudaMemcpyAsync(alpha1old, alpha1, n * sizeof(double), cudaMemcpyDeviceToDevice, s)); }
+    deltaT0_ = deltaTSave_; deltaTSave_ = deltaT_;            // [UPSTREAM] Time::operator++
     time_ += deltaT_; timeIndex++;
     if (ctl.writeInterval > 0) {
         const int wi = int(((time_ - ctl.startTime) + 0.5 * deltaT_) / ctl.writeInterval);
@@ -606,10 +652,15 @@ void ThermalCase::step(b200_step_report* rep)
     // thermo/TEqn.H
     const double rDeltaT = 1.0 / deltaT_;
     assembleBase(explicitSolve, rDeltaT);
+    // thermoScheme.H:41-68: the rDeltaT of the Sp terms is scaled by coefft = 1 + deltaT/(deltaT + deltaT0) -- runTime.deltaT0() itself,
+    // not the scheme's guarded one -- in the implicit form of the backward scheme
+    const bool bwd = backward() && !explicitSolve;
+    const double rDeltaTSp = bwd ? rDeltaT * (1.0 + deltaT_ / (deltaT_ + deltaT0_)) : rDeltaT;
     CorrectorArgs ca;
     ca.alpha1old = alpha1old; ca.diag0 = diag0; ca.source0 = source0; ca.T = T; ca.alpha1 = alpha1; ca.dFdT = dFdT; ca.T0 = T0;
     ca.diag = diag; ca.source = source; ca.thermo = d_thermo; ca.nThermo = mat.nThermo; ca.Tliq = Tliq; ca.Tsol = Tsol;
-    ca.thermoTol = ctl.thermoTolerance; ca.Tmax = ctl.Tmax > 0 ? ctl.Tmax : kVGreat; ca.rDeltaT = rDeltaT; ca.rDeltaTEuler = rDeltaT;
+    ca.thermoTol = ctl.thermoTolerance; ca.Tmax = ctl.Tmax > 0 ? ctl.Tmax : kVGreat; ca.rDeltaT = rDeltaTSp; ca.rDeltaTEuler = rDeltaT;
+    ca.kA = BackwardCoeffs{rDeltaT, 1, 1, 0, false}; ca.alpha1oldold = alpha1oldold;
     ca.rho = mat.rho; ca.Lf = mat.Lf;
     const size_t shm = 2 * (size_t)mat.nThermo * sizeof(double);
     const int grid = cells_grid(ctx, dims);
@@ -622,6 +673,9 @@ void ThermalCase::step(b200_step_report* rep)
     int nCorrDone = 0, iterSum = 0;
     double residual = 0;
     for (int tCorr = 0; tCorr < nThermoCorr; tCorr++) {
+        // TEqn.H:36-39: fvc::ddt(alpha1) with the scheme (guarded by the levels alpha.solid has at THIS call), Euler in the explicit form
+        if (bwd) ca.kA = backwardCoeffs(a1nOld);
+        touchOldTimes(false, bwd ? 2 : 1);
         if (explicitSolve) {
             { ProfScope ps_(ctx, PC_CORRECTOR); k_corrector<true><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK(); }
             perf = SolvePerf(); perf.converged = 1;

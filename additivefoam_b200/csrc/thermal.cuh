@@ -57,6 +57,10 @@ struct SidesDev {
 
 struct BoxRange { int i0, i1, j0, j1, k0, k1; };   // half-open local index box
 
+// [UPSTREAM] backwardDdtScheme coefficients: coefft = 1 + dt/(dt + dt0), coefft00 = dt*dt/(dt0*(dt + dt0)), coefft0 = coefft + coefft00.
+// Euler is {1/dt, 1, 1, 0} with `on` false (the kernels then keep the Euler expressions, operation for operation).
+struct BackwardCoeffs { double rDeltaT, coefft, coefft0, coefft00; bool on; };
+
 class ThermalCase {
 public:
     ThermalCase(Ctx* ctx, const b200_case_desc& desc);
@@ -95,6 +99,14 @@ private:
     std::vector<bool> patchUpdated;
     // time
     double time_ = 0, deltaT_ = 0;
+    double deltaT0_ = 0, deltaTSave_ = 0;        // [UPSTREAM] Time::deltaT0_, deltaTSave_ (operator++: deltaT0_ = deltaTSave_; deltaTSave_ = deltaT_)
+    // ddtScheme backward (thermoScheme.H:41-49): second old-time levels, and how many levels T / alpha.solid have so far --
+    // [UPSTREAM] backwardDdtScheme::deltaT0_(vf) is `great` while vf.nOldTimes() < 2; a level that is created later starts as a copy of
+    // the one above it (GeometricField::oldTime())
+    int TnOld = 0, a1nOld = 0;
+    bool backward() const { return ctl.ddtScheme == B200_DDT_BACKWARD; }
+    BackwardCoeffs backwardCoeffs(int nOld) const;
+    void touchOldTimes(bool ofT, int levels);
     int timeIndex = 0, writeTimeIndex = 0;
     double alphaCoNum = 0, DiNum = 0;
     // fields (device, each with one ghost plane either side; pointers address cell 0)
@@ -102,7 +114,8 @@ private:
     std::vector<double*> allocs;
     double *T = nullptr, *Told = nullptr, *alpha1 = nullptr, *alpha1old = nullptr, *alpha3 = nullptr, *kappa = nullptr,
            *rKappa = nullptr, *Cp = nullptr, *qDot = nullptr, *qDoti = nullptr, *dFdT = nullptr, *T0 = nullptr,
-           *diag0 = nullptr, *source0 = nullptr, *diag = nullptr, *source = nullptr, *upper = nullptr, *wbuf = nullptr;
+           *diag0 = nullptr, *source0 = nullptr, *diag = nullptr, *source = nullptr, *upper = nullptr, *wbuf = nullptr,
+           *Toldold = nullptr, *alpha1oldold = nullptr;
     size_t wbufCap = 0;
     double* d_thermo = nullptr;          // thermoPath table on the device: x then y
     std::unique_ptr<Ldu> ldu;
@@ -121,7 +134,7 @@ private:
     void solidificationExecute();
 
     // streamed host I/O: two copy streams beside the compute stream, one staging buffer per field and direction
-    static constexpr int NIOF = 10;
+    static constexpr int NIOF = 12;
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     double* stageIn[NIOF] = {nullptr}; double* stageOut[NIOF] = {nullptr};
     cudaEvent_t evIn[NIOF] = {nullptr}, evInFree[NIOF] = {nullptr}, evOutReady[NIOF] = {nullptr}, evOutDone[NIOF] = {nullptr};
@@ -131,7 +144,7 @@ private:
     double* field(int f);
     double* allocField();
     void haloExchange(double* f);
-    void updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1);
+    void updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1, bool propertiesOnly = false);
     void setDeltaT(double alphaCoMax, double diMax);
     void updateSources();
     void qDotOnce(heatSourceModel& hs, double* target, double dt, double sumDt, bool accumulate);

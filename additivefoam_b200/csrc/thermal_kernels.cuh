@@ -58,7 +58,8 @@ __device__ __forceinline__ double poly3(const double* v, double x)
 __global__ void __launch_bounds__(BLK) k_props(BlockDims d, MatDev m, const double* __restrict__ T, const double* __restrict__ Told,
                                                const double* __restrict__ alpha1, double* __restrict__ alpha3, double* __restrict__ kappa,
                                                double* __restrict__ rKappa, double* __restrict__ Cp, double rDeltaT, double deltaT,
-                                               RedWork red)
+                                               RedWork red, BackwardCoeffs kb = BackwardCoeffs{0, 1, 1, 0, false},
+                                               const double* __restrict__ Toldold = nullptr)
 {
     double mxA = -1e300, mnA1 = 1e300;
     B200_FOR_CELLS(d)
@@ -73,7 +74,9 @@ __global__ void __launch_bounds__(BLK) k_props(BlockDims d, MatDev m, const doub
         const double kap = (1.0 - a3) * (a1 * poly3(m.kappa[0], T1) + a2 * poly3(m.kappa[1], T2)) + a3 * poly3(m.kappa[2], T1);
         const double cp = (1.0 - a3) * (a1 * poly3(m.Cp[0], T1) + a2 * poly3(m.Cp[1], T2)) + a3 * poly3(m.Cp[2], T1);
         kappa[c] = kap; rKappa[c] = 1.0 / kap; Cp[c] = cp;
-        mxA = fmax(mxA, fabs(rDeltaT * (Tc - Told[c])) / (m.Tliq - m.Tsol) * deltaT);
+        // setDeltaT.H:6-11 fvc::ddt(T): Euler, or backward rDeltaT*(coefft*T - coefft0*T.oldTime() + coefft00*T.oldTime().oldTime())
+        const double ddtT = kb.on ? kb.rDeltaT * (kb.coefft * Tc - kb.coefft0 * Told[c] + kb.coefft00 * Toldold[c]) : rDeltaT * (Tc - Told[c]);
+        mxA = fmax(mxA, fabs(ddtT) / (m.Tliq - m.Tsol) * deltaT);
         mnA1 = fmin(mnA1, a1);
     }
     __shared__ double smem[32];
@@ -198,7 +201,8 @@ __global__ void k_side_evaluate(BlockDims d, int s, int type, double fixedValue,
 // thermoScheme.H:34-39, implicit: diag0 = rho*Cp*V/dt + sum(off-diagonals), source0 = rho*Cp*V/dt*Told + V*qDot
 __global__ void __launch_bounds__(BLK) k_assemble_implicit(BlockDims d, Geom g, const double* __restrict__ Cp, const double* __restrict__ Told,
                                                            const double* __restrict__ qDot, const double* __restrict__ upper,
-                                                           double* __restrict__ diag0, double* __restrict__ source0, double rDeltaT, double rho)
+                                                           double* __restrict__ diag0, double* __restrict__ source0, double rDeltaT, double rho,
+                                                           BackwardCoeffs kb = BackwardCoeffs{0, 1, 1, 0, false}, const double* __restrict__ Toldold = nullptr)
 {
     B200_FOR_CELLS(d)
     {
@@ -216,8 +220,13 @@ __global__ void __launch_bounds__(BLK) k_assemble_implicit(BlockDims d, Geom g, 
         if (fx >= 0) ld += upper[fx];
         if (fy >= 0) ld += upper[fy];
         if (fz >= 0) ld += upper[fz];
-        diag0[c] = (rDeltaT * g.V) * rhoCp - ld;
-        source0[c] = (rDeltaT * Told[c] * g.V) * rhoCp + g.V * qDot[c];
+        if (kb.on) {    // [UPSTREAM] backwardDdtScheme::fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*old - coefft00*oldOld)
+            diag0[c] = ((kb.coefft * kb.rDeltaT) * g.V) * rhoCp - ld;
+            source0[c] = (kb.rDeltaT * g.V * (kb.coefft0 * Told[c] - kb.coefft00 * Toldold[c])) * rhoCp + g.V * qDot[c];
+        } else {
+            diag0[c] = (rDeltaT * g.V) * rhoCp - ld;
+            source0[c] = (rDeltaT * Told[c] * g.V) * rhoCp + g.V * qDot[c];
+        }
     }
 }
 
@@ -277,6 +286,8 @@ struct CorrectorArgs {
     double *T, *alpha1, *dFdT, *T0, *diag, *source;
     const double* thermo; int nThermo;
     double Tliq, Tsol, thermoTol, Tmax, rDeltaT, rDeltaTEuler, rho, Lf;
+    BackwardCoeffs kA;              // fvc::ddt(alpha1) of TEqn.H:36-39 when the scheme is backward (kA.on), else the Euler form
+    const double* alpha1oldold;
 };
 
 template <bool EXPLICIT>
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
     const double slope = 1e10;
     const double s2 = a.rDeltaT * a.rho * a.Lf;
     double mxRes = -1e300;
-    auto cell = [&](int i, int j, int k, int64_t c, double x, double y, double aold, double d0, double s0) {
+    auto cell = [&](int i, int j, int k, int64_t c, double x, double y, double aold, double d0, double s0, double aoo) {
         double dF, t0;
         if (x < a.Tliq && x > a.Tsol) {
             int lo = 0;
@@ -311,7 +322,8 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         const double source1 = (g.V * (Acoef * a.Tmax)) * a.rDeltaT;
         const double diag2 = (g.V * dF) * s2;
         const double source2 = (g.V * (dF * t0)) * s2;
-        const double su = (a.rho * a.Lf) * (a.rDeltaTEuler * (y - aold));
+        const double su = a.kA.on ? (a.rho * a.Lf) * (a.kA.rDeltaT * (a.kA.coefft * y - a.kA.coefft0 * aold + a.kA.coefft00 * aoo))
+                                  : (a.rho * a.Lf) * (a.rDeltaTEuler * (y - aold));
         const double sourceR = source2 - g.V * su;
         double dg = (d0 + diag1) - diag2;
         double sr = (s0 + source1) - sourceR;
@@ -343,11 +355,12 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         const int rowB = itemB / segs, iB = (itemB - rowB * segs) * BLK + threadIdx.x;
         const bool okA = iA < d.nx, okB = itemB < nItems && iB < d.nx;
         const int64_t cA = (int64_t)rowA * d.nx + iA, cB = (int64_t)rowB * d.nx + iB;
-        double xA = 0, yA = 0, oA = 0, dA = 0, sA = 0, xB = 0, yB = 0, oB = 0, dB = 0, sB = 0;
+        double xA = 0, yA = 0, oA = 0, dA = 0, sA = 0, xB = 0, yB = 0, oB = 0, dB = 0, sB = 0, ooA = 0, ooB = 0;
         if (okA) { xA = ld_first_rw(a.T + cA); yA = ld_first_rw(a.alpha1 + cA); oA = ld_first(a.alpha1old + cA); dA = ld_first(a.diag0 + cA); sA = ld_first(a.source0 + cA); }
         if (okB) { xB = ld_first_rw(a.T + cB); yB = ld_first_rw(a.alpha1 + cB); oB = ld_first(a.alpha1old + cB); dB = ld_first(a.diag0 + cB); sB = ld_first(a.source0 + cB); }
-        if (okA) { const int k = rowA / d.ny; cell(iA, rowA - k * d.ny, k, cA, xA, yA, oA, dA, sA); }
-        if (okB) { const int k = rowB / d.ny; cell(iB, rowB - k * d.ny, k, cB, xB, yB, oB, dB, sB); }
+        if (a.kA.on) { if (okA) ooA = ld_first(a.alpha1oldold + cA); if (okB) ooB = ld_first(a.alpha1oldold + cB); }
+        if (okA) { const int k = rowA / d.ny; cell(iA, rowA - k * d.ny, k, cA, xA, yA, oA, dA, sA, ooA); }
+        if (okB) { const int k = rowB / d.ny; cell(iB, rowB - k * d.ny, k, cB, xB, yB, oB, dB, sB, ooB); }
     }
     if (EXPLICIT) {
         __shared__ double smem[32];

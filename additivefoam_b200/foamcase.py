@@ -345,7 +345,7 @@ def _read_controls(case_dir):
     if int(pimple.get("nOuterCorrectors", 0)) > 0:
         raise FoamCaseError("PIMPLE nOuterCorrectors > 0 asks for the pU loop and fvm::div(phi,T) with phi != 0, which the library "
                             "does not implement (thermal path only)")
-    _check_schemes(case_dir)
+    ddt_scheme = _check_schemes(case_dir)
     adjustable = c.get("writeControl") == "adjustableRunTime"
     return dict(startTime=float(c.get("startTime", 0.0)), endTime=float(c["endTime"]), deltaT=float(c["deltaT"]),
                 adjustTimeStep=_switch(c["adjustTimeStep"], "adjustTimeStep") if "adjustTimeStep" in c else 0,
@@ -355,7 +355,8 @@ def _read_controls(case_dir):
                 thermoTolerance=float(pimple.get("thermoTolerance", 1e-6)), Tmax=float(pimple.get("Tmax", 0.0)),
                 explicitSolve=_switch(pimple["explicitSolve"], "explicitSolve") if "explicitSolve" in pimple else 0,
                 solver=_SOLVERS[ts["solver"]], preconditioner=_PRECONDS[precond], tolerance=float(ts.get("tolerance", 1e-6)),
-                relTol=float(ts.get("relTol", 0.0)), minIter=int(ts.get("minIter", 0)), maxIter=int(ts.get("maxIter", 1000)))
+                relTol=float(ts.get("relTol", 0.0)), minIter=int(ts.get("minIter", 0)), maxIter=int(ts.get("maxIter", 1000)),
+                ddtScheme=ddt_scheme)
 
 
 def _scheme(d, section, *keys):
@@ -376,10 +377,10 @@ def _check_schemes(case_dir):
     if not os.path.exists(path):
         raise FoamCaseError("system/fvSchemes is missing")
     d = parse_dictionary(_read(case_dir, "system", "fvSchemes"))
-    ddt = _scheme(d, "ddtSchemes", "ddt(T)")
-    if ddt not in ("Euler",):
-        raise FoamCaseError(f"ddtSchemes {ddt!r}: read_case wires the Euler scheme only (backward is available through the case "
-                            "description's controls['ddtScheme']; CrankNicolson is not implemented)")
+    # thermoScheme.H:2 looks the scheme up by the field's name: mesh.schemes().ddt("T") -> the entry `T` if there is one, else `default`
+    ddt = _scheme(d, "ddtSchemes", "T")
+    if ddt not in ("Euler", "backward"):
+        raise FoamCaseError(f"ddtSchemes {ddt!r}: Euler and backward are implemented (thermoScheme.H:41-49); CrankNicolson is not")
     # `laplacian(kappa,T)` is one word to OpenFOAM but a word plus a list to this module's grammar: look for it in the text itself
     text = re.sub(r"//[^\n]*|/\*.*?\*/", "", _read(case_dir, "system", "fvSchemes"), flags=re.S)
     m = re.search(r"laplacian\(\s*kappa\s*,\s*T\s*\)\s+([^;]+);", text)
@@ -389,6 +390,7 @@ def _check_schemes(case_dir):
     interp = _scheme(d, "interpolationSchemes")
     if interp != "linear":
         raise FoamCaseError(f"interpolationSchemes default {interp!r}: the diffusion-number kernel implements linear interpolation")
+    return abi.DDT_BACKWARD if ddt == "backward" else abi.DDT_EULER
 
 
 def _read_powder(case_dir, mesh):

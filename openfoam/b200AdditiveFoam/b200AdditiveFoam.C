@@ -11,7 +11,7 @@
 
   What the resident step does not implement is refused up front instead of being approximated (the reference accepts more):
     * flow coupling: PIMPLE nOuterCorrectors > 0 (pU/UEqn.H, pU/pEqn.H, fvm::div(phi, T) with phi != 0)
-    * ddtSchemes other than Euler (thermoScheme.H:41-68 backward / CrankNicolson)
+    * ddtSchemes CrankNicolson (thermoScheme.H:51-65; Euler and backward are implemented)
     * laplacian(kappa,T) other than Gauss harmonic, meshes that are not one uniform blockMesh hex block,
       patch types other than zeroGradient / fixedValue (uniform) / mixedTemperature, decompositions other than z-slabs
 
@@ -108,9 +108,10 @@ int main(int argc, char *argv[])
     {
         refuse("PIMPLE nOuterCorrectors > 0 (flow coupling)");
     }
-    if (word(mesh.schemesDict().subDict("ddtSchemes").lookup("default")) != "Euler")
+    const word ddtScheme(mesh.schemesDict().subDict("ddtSchemes").lookup("default"));      // thermoScheme.H:2 (no per-field entry in the tutorials)
+    if (ddtScheme != "Euler" && ddtScheme != "backward")
     {
-        refuse("ddtSchemes other than Euler");
+        refuse("ddtSchemes other than Euler and backward");
     }
     {
         const dictionary& lap = mesh.schemesDict().subDict("laplacianSchemes");
@@ -286,6 +287,7 @@ int main(int argc, char *argv[])
         ct.minIter = sd.lookupOrDefault<label>("minIter", 0);
         ct.maxIter = sd.lookupOrDefault<label>("maxIter", 1000);
     }
+    ct.ddtScheme = ddtScheme == "backward" ? B200_DDT_BACKWARD : B200_DDT_EULER;
     desc.Tinitial = gAverage(T.primitiveField());       // overwritten below by the field itself
     desc.powderZMin = 1e300;                            // alpha.powder comes from the file, see below
 

@@ -206,6 +206,8 @@ static Field* fieldOf(RankState& s, int f)
     case B200_FIELD_T0: return &s.T0;
     case B200_FIELD_T_OLD: return &s.Told;
     case B200_FIELD_ALPHA_SOLID_OLD: return &s.alpha1old;
+    case B200_FIELD_T_OLD_OLD: return &s.Toldold;
+    case B200_FIELD_ALPHA_SOLID_OLD_OLD: return &s.alpha1oldold;
     }
     return nullptr;
 }
@@ -328,6 +330,14 @@ int afo_case_patch_state(void* h, int p, scalar* Tb, scalar* valueFraction)
     const Patch& pa = ((Case*)h)->rk[0].mesh.patches[p];
     if (Tb) std::copy(pa.Tb.begin(), pa.Tb.end(), Tb);
     if (valueFraction) std::copy(pa.valueFraction.begin(), pa.valueFraction.end(), valueFraction);
+    return 0;
+}
+// Test probe: the time-scheme state the reference's TEqn sees in the NEXT step -- deltaT0 after the coming runTime++ (= the deltaT
+// saved at the last one) and the number of old-time levels T and alpha.solid have ([UPSTREAM] GeometricField::nOldTimes)
+int afo_case_time_scheme_state(void* h, scalar* deltaTSave, int* TnOld, int* a1nOld)
+{
+    Case* c = (Case*)h;
+    *deltaTSave = c->deltaTSave; *TnOld = c->TnOld; *a1nOld = c->a1nOld;
     return 0;
 }
 scalar afo_mixed_value_fraction(scalar h, scalar emissivity, scalar Tinf, scalar Tp, scalar kap, scalar deltaCoeff)

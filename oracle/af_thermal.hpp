@@ -181,6 +181,7 @@ struct HeatSource {
 struct RankState {
     Mesh mesh;
     Field T, Told, alpha1, alpha1old, alpha3, kappa, Cp, qDot, dFdT, T0;
+    Field Toldold, alpha1oldold;        // second old-time level (ddtScheme backward)
     bool alpha1HasOld = false;
     // base TEqn, built once per step (thermoScheme.H)
     LduMatrix teqn;                     // diag, upper (implicit) + bouCoeffs for processor patches
@@ -199,7 +200,24 @@ struct Case {
     std::vector<HeatSource> sources;
     scalar Tliq = 0, Tsol = 0;
     // Time ([UPSTREAM] OpenFOAM/db/Time)
-    scalar time = 0, deltaT = 0, deltaT0 = 0;
+    scalar time = 0, deltaT = 0, deltaT0 = 0, deltaTSave = 0;          // [UPSTREAM] Time::deltaT_, deltaT0_, deltaTSave_
+    // [UPSTREAM] GeometricField old-time levels exist only once asked for (oldTime() creates a level as a copy of the one above it):
+    // how many T and alpha.solid have -- backwardDdtScheme::deltaT0_(vf) returns great while vf.nOldTimes() < 2
+    int TnOld = 0, a1nOld = 0;
+    bool backward() const { return d.controls.ddtScheme == B200_DDT_BACKWARD; }
+    struct BackwardCoeffs { scalar rDeltaT, coefft, coefft0, coefft00; };
+    // [UPSTREAM] backwardDdtScheme: coefft = 1 + dt/(dt + dt0), coefft00 = dt*dt/(dt0*(dt + dt0)), coefft0 = coefft + coefft00
+    BackwardCoeffs backwardCoeffs(int nOld) const
+    {
+        const scalar dt0 = nOld < 2 ? 1.0e15 : deltaT0;
+        BackwardCoeffs k;
+        k.rDeltaT = 1.0 / deltaT;
+        k.coefft = 1 + deltaT / (deltaT + dt0);
+        k.coefft00 = deltaT * deltaT / (dt0 * (deltaT + dt0));
+        k.coefft0 = k.coefft + k.coefft00;
+        return k;
+    }
+    void touchOldTimes(bool ofT, int levels);
     label timeIndex = 0, writeTimeIndex = 0;
     scalar alphaCoNum = 0, DiNum = 0;
     bool verbose = false;
@@ -259,7 +277,7 @@ inline void Case::init(const b200_case_desc& desc, int nRanks)
         RankState& s = rk[r];
         buildMesh(s.mesh, d, r, R);
         const label n = s.mesh.nCells();
-        s.T.assign(n, d.Tinitial); s.Told = s.T;
+        s.T.assign(n, d.Tinitial); s.Told = s.T; s.Toldold = s.T;
         s.alpha1.assign(n, 0); s.alpha3.assign(n, 0);
         for (label c = 0; c < n; c++) {
             // createFields.H:74-78
@@ -268,11 +286,12 @@ inline void Case::init(const b200_case_desc& desc, int nRanks)
             // setFields box on alpha.powder (tutorials/multiLayerPBF/system/setFieldsDict:18-29)
             if (s.mesh.C(c).z > d.powderZMin) s.alpha3[c] = 1.0;
         }
-        s.alpha1old = s.alpha1;
+        s.alpha1old = s.alpha1; s.alpha1oldold = s.alpha1;
         s.kappa.assign(n, 0); s.Cp.assign(n, 0); s.qDot.assign(n, 0); s.dFdT.assign(n, 0); s.T0 = s.T;
         s.teqn.addr = &s.mesh.addr; s.teqn.interfaces = &s.mesh.interfaces;
     });
-    time = d.controls.startTime; deltaT = d.controls.deltaT; deltaT0 = deltaT; timeIndex = 0; writeTimeIndex = 0;
+    time = d.controls.startTime; deltaT = d.controls.deltaT; deltaT0 = deltaT; deltaTSave = deltaT; timeIndex = 0; writeTimeIndex = 0;
+    TnOld = 0; a1nOld = 0;
     sources.resize(d.nBeams);
     for (int b = 0; b < d.nBeams; b++) {
         const b200_beam& bs = d.beams[b];
@@ -385,17 +404,31 @@ inline scalar Case::surfaceSumDiMax()
 }
 
 // SOLVER/setDeltaT.H:1-50 + [UPSTREAM] Time::setDeltaT -> Time::adjustDeltaT (write-time snapping)
+// [UPSTREAM] GeometricField::oldTime(): a level that does not exist yet is created as a copy of the level above it
+inline void Case::touchOldTimes(bool ofT, int levels)
+{
+    int& n = ofT ? TnOld : a1nOld;
+    if (n < 2 && levels >= 2) forRanks(R, [&](int r) { if (ofT) rk[r].Toldold = rk[r].Told; else rk[r].alpha1oldold = rk[r].alpha1old; });
+    n = std::max(n, levels);
+}
+
 inline void Case::setDeltaT()
 {
     const b200_controls& ct = d.controls;
     if (!ct.adjustTimeStep) return;
     std::vector<scalar> pm(R, 0.0);
     const scalar rDeltaT = 1.0 / deltaT;
+    // setDeltaT.H:6-11 fvc::ddt(T) with the scheme of fvSchemes: Euler rDeltaT*(T - T.oldTime()), or backward
+    const BackwardCoeffs kb = backwardCoeffs(TnOld);
+    touchOldTimes(true, backward() ? 2 : 1);
     forRanks(R, [&](int r) {
         RankState& s = rk[r];
         scalar mx = -vGreat;
-        for (label c = 0; c < s.mesh.nCells(); c++)
-            mx = std::max(mx, std::fabs(rDeltaT * (s.T[c] - s.Told[c])) / (Tliq - Tsol) * deltaT);
+        for (label c = 0; c < s.mesh.nCells(); c++) {
+            const scalar ddtT = backward() ? kb.rDeltaT * (kb.coefft * s.T[c] - kb.coefft0 * s.Told[c] + kb.coefft00 * s.Toldold[c])
+                                           : rDeltaT * (s.T[c] - s.Told[c]);
+            mx = std::max(mx, std::fabs(ddtT) / (Tliq - Tsol) * deltaT);
+        }
         pm[r] = mx;
     });
     alphaCoNum = -vGreat;
@@ -531,6 +564,10 @@ inline void Case::assembleBase(bool explicitSolve)
     const scalar rDeltaT = 1.0 / deltaT;
     const scalar rho = d.material.rho;
     forRanks(R, [&](int r) { updateCoeffsT(r); });     // fvMatrix(T, ...) ctor -> T.boundaryFieldRef().updateCoeffs()
+    // thermoScheme.H:25-39: the explicit form always uses EulerDdtScheme; the implicit one fvm::ddt(T) with the scheme of fvSchemes
+    const bool bwd = backward() && !explicitSolve;
+    const BackwardCoeffs kT = backwardCoeffs(TnOld);
+    touchOldTimes(true, bwd ? 2 : 1);
     forRanks(R, [&](int r) {
         RankState& s = rk[r];
         const Mesh& m = s.mesh;
@@ -539,8 +576,13 @@ inline void Case::assembleBase(bool explicitSolve)
         s.teqn.diag.resize(n); s.source.resize(n);
         for (label c = 0; c < n; c++) {
             const scalar rhoCp = rho * s.Cp[c];
-            s.teqn.diag[c] = (rDeltaT * m.V) * rhoCp;
-            s.source[c] = (rDeltaT * s.Told[c] * m.V) * rhoCp;
+            if (bwd) {      // [UPSTREAM] backwardDdtScheme::fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*old - coefft00*oldOld)
+                s.teqn.diag[c] = ((kT.coefft * kT.rDeltaT) * m.V) * rhoCp;
+                s.source[c] = (kT.rDeltaT * m.V * (kT.coefft0 * s.Told[c] - kT.coefft00 * s.Toldold[c])) * rhoCp;
+            } else {
+                s.teqn.diag[c] = (rDeltaT * m.V) * rhoCp;
+                s.source[c] = (rDeltaT * s.Told[c] * m.V) * rhoCp;
+            }
         }
         s.internalCoeffs.resize(m.patches.size()); s.boundaryCoeffs.resize(m.patches.size());
         s.teqn.bouCoeffs.assign(m.interfaces.size(), Field());
@@ -653,6 +695,10 @@ inline void Case::thermoSource(int r)
 inline SolverPerf Case::solveCorrector(bool explicitSolve, scalar rDeltaT, scalar rDeltaTEuler)
 {
     const scalar rho = d.material.rho, Lf = d.material.Lf;
+    // TEqn.H:36-39: Euler fvcDdt(alpha1) when ddtScheme == "Euler" (always so in the explicit form, thermoScheme.H:22), else fvc::ddt
+    const bool bwdA = backward() && !explicitSolve;
+    const BackwardCoeffs kA = backwardCoeffs(a1nOld);
+    touchOldTimes(false, bwdA ? 2 : 1);
     const scalar Tmax = d.controls.Tmax > 0 ? d.controls.Tmax : vGreat;
     std::vector<LduMatrix> A(R);
     Fields totalSource(R), psi(R);
@@ -670,7 +716,8 @@ inline SolverPerf Case::solveCorrector(bool explicitSolve, scalar rDeltaT, scala
             const scalar source1 = (m.V * (Acoef * Tmax)) * rDeltaT;
             const scalar diag2 = (m.V * s.dFdT[c]) * s2;
             const scalar source2 = (m.V * (s.dFdT[c] * s.T0[c])) * s2;
-            const scalar su = (rho * Lf) * (rDeltaTEuler * (s.alpha1[c] - s.alpha1old[c]));
+            const scalar su = bwdA ? (rho * Lf) * (kA.rDeltaT * (kA.coefft * s.alpha1[c] - kA.coefft0 * s.alpha1old[c] + kA.coefft00 * s.alpha1oldold[c]))
+                                   : (rho * Lf) * (rDeltaTEuler * (s.alpha1[c] - s.alpha1old[c]));
             const scalar sourceR = source2 - m.V * su;
             M.diag[c] = (M.diag[c] + diag1) - diag2;
             totalSource[r][c] = (totalSource[r][c] + source1) - sourceR;
@@ -868,8 +915,15 @@ inline void Case::step(b200_step_report* rep)
     setDeltaT();                                        // :72
     updateSources();                                    // :74
     // runTime++ (:76): store old-time fields, advance time
-    forRanks(R, [&](int r) { rk[r].Told = rk[r].T; rk[r].alpha1old = rk[r].alpha1; });
-    deltaT0 = deltaT;
+    // ([UPSTREAM] GeometricField::storeOldTimes shifts the levels that exist; a level created later is a copy of the one above it at
+    // that moment, see touchOldTimes)
+    forRanks(R, [&](int r) {
+        RankState& s = rk[r];
+        if (TnOld >= 2) s.Toldold = s.Told;
+        if (a1nOld >= 2) s.alpha1oldold = s.alpha1old;
+        s.Told = s.T; s.alpha1old = s.alpha1;
+    });
+    deltaT0 = deltaTSave; deltaTSave = deltaT;          // [UPSTREAM] Time::operator++
     time += deltaT; timeIndex++;
     if (ct.writeInterval > 0) {                         // [UPSTREAM] Time::operator++ write-time bookkeeping
         const label wi = label(((time - ct.startTime) + 0.5 * deltaT) / ct.writeInterval);
@@ -894,14 +948,17 @@ inline void Case::step(b200_step_report* rep)
     if (explicitSolve) explicitSolve = (surfaceSumDiMax() * deltaT < 1.0);
     // thermo/TEqn.H
     assembleBase(explicitSolve);
-    const scalar rDeltaT = 1.0 / deltaT;                // Euler: coefft = 1
+    // thermoScheme.H:41-68: rDeltaT of the Sp terms is scaled by coefft = 1 + deltaT/(deltaT + deltaT0) for backward -- with
+    // runTime.deltaT0() itself, not the scheme's guarded one -- in the implicit form only
+    scalar rDeltaT = 1.0 / deltaT;
+    if (backward() && !explicitSolve) rDeltaT *= 1.0 + deltaT / (deltaT + deltaT0);
     forRanks(R, [&](int r) { std::fill(rk[r].dFdT.begin(), rk[r].dFdT.end(), 0.0); rk[r].T0 = rk[r].T; });
     int nCorrDone = 0, iterSum = 0;
     scalar residual = 0;
     SolverPerf perf;
     for (int tCorr = 0; tCorr < nThermoCorr; tCorr++) {
         forRanks(R, [&](int r) { thermoSource(r); });
-        perf = solveCorrector(explicitSolve, rDeltaT, rDeltaT);
+        perf = solveCorrector(explicitSolve, rDeltaT, 1.0 / deltaT);
         iterSum += perf.nIterations;
         // TEqn.H:44 T.correctBoundaryConditions() -- a SECOND evaluate after the one at the end of solveSegregated: the patches are
         // no longer "updated", so mixedTemperature recomputes its value fraction from the face temperatures the first evaluate

@@ -36,6 +36,15 @@ def configs():
     out["track_tmax"] = (c, 40)
     c = cases.multi_layer_pbf(n=(32, 16, 10), nHatch=2, writeInterval=0.0, deltaT=1e-6)        # fixedValue walls, powder layer
     out["pbf"] = (c, 30)
+    # ddtSchemes default backward (thermoScheme.H:41-49): backward fvm::ddt(T) and fvc::ddt(alpha1), rDeltaT of the Sp terms scaled by coefft
+    c = cases.amb2018_02_b(n=(40, 10, 6), writeInterval=0.0, explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC,
+                           ddtScheme=abi.DDT_BACKWARD)
+    out["amb_backward_pcg"] = (c, 25)
+    c = cases.synthetic_track((36, 12, 8), writeInterval=0.0, deltaT=2e-6, Tmax=2500.0, nThermoCorrectors=6, thermoTolerance=1e-6,
+                              explicitSolve=0, maxDi=20.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC, ddtScheme=abi.DDT_BACKWARD)
+    out["track_backward_tmax"] = (c, 40)
+    c = cases.multi_layer_pbf(n=(32, 16, 10), nHatch=2, writeInterval=0.0, deltaT=1e-6, ddtScheme=abi.DDT_BACKWARD)
+    out["pbf_backward"] = (c, 30)
     for case, _ in out.values():
         for b in case["beams"]:
             b["hitPathIntervals"] = 0
@@ -87,8 +96,20 @@ def digest(a):
 
 
 def step_inputs(o, case, abi):
-    """State the fragment sees in the step that `o.step()` is about to take: call BEFORE the step for the start-of-step fields."""
-    return dict(T=o.field(abi.FIELD_T), alpha1=o.field(abi.FIELD_ALPHA_SOLID), patches=[tb.copy() for tb, _ in o.patch_state()])
+    """State the fragment sees in the step that `o.step()` is about to take: call BEFORE the step for the start-of-step fields.
+    After runTime++ the first old-time level of T and alpha.solid is the start-of-step field and the second one (backward scheme) the
+    first level of before; alpha.solid has no levels at all until its first fvc::ddt (the fragment then creates them, and the scheme
+    uses deltaT0 = great for that one call); deltaT0 is the deltaT saved at the previous runTime++."""
+    dt_save, TnOld, a1nOld = o.time_scheme_state()
+    backward = case["controls"]["ddtScheme"] == abi.DDT_BACKWARD
+    T, A = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
+    T_levels, A_levels = [T], [A]
+    if backward:
+        T_levels = [T, o.field(abi.FIELD_T_OLD)]
+        assert a1nOld in (0, 2)
+        A_levels = [] if a1nOld == 0 else [A, o.field(abi.FIELD_ALPHA_SOLID_OLD)]
+    return dict(T=T, alpha1=A, T_levels=T_levels, A_levels=A_levels, deltaT0=dt_save, ddt="backward" if backward else "Euler",
+                patches=[tb.copy() for tb, _ in o.patch_state()])
 
 
 def main():
@@ -99,7 +120,6 @@ def main():
     out = {}
     for name, (case, steps) in configs().items():
         o = ol.OracleCase(case)
-        dt0 = case["controls"]["deltaT"]
         rows = []
         worst = 0.0
         for s in range(steps):
@@ -107,16 +127,15 @@ def main():
             rep = o.step()
             kappa, Cp, qDot = (o.field(f) for f in (abi.FIELD_KAPPA, abi.FIELD_CP, abi.FIELD_QDOT))
             # after runTime++ the old-time level of T and alpha.solid is the start-of-step field
-            req = request(case, "Euler", rep.explicitStep, rep.deltaT, dt0, o.L.afo_case_Tliq(o.h), o.L.afo_case_Tsol(o.h),
+            req = request(case, pre["ddt"], rep.explicitStep, rep.deltaT, pre["deltaT0"], o.L.afo_case_Tliq(o.h), o.L.afo_case_Tsol(o.h),
                           case["controls"]["nThermoCorrectors"] if (rep.totalPower > 1e-15 or pre["alpha1"].min() < 1 - 1e-15) else 1,
-                          pre["T"], [pre["T"]], pre["alpha1"], [pre["alpha1"]], kappa, Cp, qDot, pre["patches"])
+                          pre["T"], pre["T_levels"], pre["alpha1"], pre["A_levels"], kappa, Cp, qDot, pre["patches"])
             its, T, A, Tb, vf = parse(run_ref(req), len(case["patches"]))
             To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
             worst = max(worst, float(np.max(np.abs(T - To)) / np.max(np.abs(To))), float(np.max(np.abs(A - Ao))))
             for (tbo, vfo), tbr, vfr in zip(o.patch_state(), Tb, vf):
                 worst = max(worst, float(np.max(np.abs(tbo - tbr)) / np.max(np.abs(tbr))), float(np.max(np.abs(vfo - vfr))))
             rows.append({"iters": its, "T": digest(T), "alpha1": digest(A), "Tb": [digest(t) for t in Tb], "valueFraction": [digest(v) for v in vf]})
-            dt0 = rep.deltaT
         out[name] = rows
         print(name, "steps", steps, "correctors of the last step", len(rows[-1]["iters"]), "oracle vs reference text (T, alpha.solid, patch values, value fractions), worst:", worst)
     with open(os.path.join(HERE, "ref_teqn.json"), "w") as f:

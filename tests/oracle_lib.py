@@ -42,6 +42,7 @@ def load():
     L.afo_case_sources_probe.argtypes = [C.c_void_p, C.c_double, dp]
     L.afo_case_pre_step_state.argtypes = [C.c_void_p, dp]
     L.afo_case_reset_alpha_solid.argtypes = [C.c_void_p]
+    L.afo_case_time_scheme_state.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.afo_case_n_patches.argtypes = [C.c_void_p]
     L.afo_case_patch_size.restype = C.c_int64
     L.afo_case_patch_size.argtypes = [C.c_void_p, C.c_int]
@@ -117,6 +118,12 @@ class OracleCase:
 
     def reset_alpha_solid(self):
         assert self.L.afo_case_reset_alpha_solid(self.h) == 0
+
+    def time_scheme_state(self):
+        """(deltaT0 the next step's TEqn will see, old-time levels of T, of alpha.solid)."""
+        dts, a, b = C.c_double(0.0), C.c_int(0), C.c_int(0)
+        self.L.afo_case_time_scheme_state(self.h, C.byref(dts), C.byref(a), C.byref(b))
+        return dts.value, a.value, b.value
 
     def pre_step_state(self):
         """updateProperties() (so that kappa, Cp are what the next step's controls see) and T.oldTime()."""
