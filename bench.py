@@ -43,7 +43,9 @@ def parse():
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--no-weak", action="store_true", help="skip the weak-scaled sub-record (N > 1, --scaling strong)")
     ap.add_argument("--no-parity-check", action="store_true")
-    ap.add_argument("--workload", default="track", choices=["track", "rosenthal"])
+    ap.add_argument("--workload", default="track", choices=["track", "rosenthal", "multibeam", "pbf"],
+                    help="track: BASELINE configs[2] (the benchmarked one); rosenthal: configs[1]; multibeam: configs[3] (use --nx 1000 --ny 250 --nz 200); "
+                         "pbf: configs[4] (--nx 1000 --ny 500 --nz 400, 8 GPUs)")
     ap.add_argument("--explicit", action="store_true", help="as-shipped mode of configs[0]: explicitSolve true, maxDi 1 (diagonal solves only)")
     ap.add_argument("--solver", default="PCG", choices=["PCG", "PBiCGStab"])
     ap.add_argument("--preconditioner", default="DIC", choices=["DIC", "DILU", "diagonal", "none"])
@@ -64,15 +66,22 @@ def make_case(args, nz, pre_steps_dt=2e-5):
         ctl.update(explicitSolve=1, maxDi=1.0, deltaT=2e-6)
     if args.workload == "rosenthal":
         return cases.rosenthal(n, **ctl)
+    if args.workload == "multibeam":
+        return cases.multi_beam(n, **ctl)
+    if args.workload == "pbf":
+        ctl.pop("maxDi")                   # configs[4]: maxDi 100 (tutorials/multiLayerPBF/system/controlDict:52), Tmax 3300
+        return cases.multi_layer_pbf(n, **ctl)
     return cases.synthetic_track(n, **ctl)
 
 
 def workload_name(args, nz):
-    kind = "conduction-only Rosenthal track" if args.workload == "rosenthal" else "conduction+solidification track"
+    kind = {"rosenthal": "conduction-only Rosenthal track", "multibeam": "four beams, two of them transient (BASELINE configs[3])",
+            "pbf": "powder layer, raster scan, transient modifiedSuperGaussian beam, Tmax 3300 (BASELINE configs[4])"}.get(
+        args.workload, "conduction+solidification track")
     if args.explicit:
         kind += ", explicitSolve true / maxDi 1 (as-shipped mode)"
-    return (f"synthetic uniform-hex {args.nx}x{args.ny}x{nz} cells (20 um), single superGaussian beam, {kind}, implicit "
-            f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20 (BASELINE configs[2])")
+    return (f"synthetic uniform-hex {args.nx}x{args.ny}x{nz} cells (20 um), {"single superGaussian beam, " if args.workload in ("track", "rosenthal") else ""}{kind}, implicit "
+            f"{args.solver}/{args.preconditioner} tol 1e-15 maxIter 20" + (" (BASELINE configs[2])" if args.workload == "track" else ""))
 
 
 def global_nz(args, world):

@@ -77,9 +77,13 @@ def random_case(seed):
                 Tinitial=t_init, powderZMin=float(rng.choice([1e300, -0.4 * lz])))
 
 
-@pytest.mark.parametrize("seed", range(24))
+@pytest.mark.parametrize("seed", list(range(24)) + [100 + s for s in range(10)])
 def test_random_case_matches_oracle(ctx, oracle, seed):
-    case = random_case(seed)
+    """Seeds >= 100: the same generator with ddtSchemes backward (thermoScheme.H:41-49) -- second old-time levels, the scheme's fvc::ddt
+    in setDeltaT.H and TEqn.H, explicit steps (always Euler) mixed in where the case asks for explicitSolve."""
+    case = random_case(seed % 100)
+    if seed >= 100:
+        case["controls"]["ddtScheme"] = abi.DDT_BACKWARD
     g, o = lib.Case(ctx, case), ol.OracleCase(case, lib=oracle)
     for s in range(25):
         rg, ro = g.step(), o.step()
