@@ -55,7 +55,7 @@ int b200_ctx_create(int device_ordinal, const void* nccl_unique_id, int rank, in
 int b200_ctx_destroy(b200_ctx* ctx)
 {
     B200_TRY
-    if (ctx) { delete ctx->p; delete ctx; }
+    if (ctx) { cudaSetDevice(ctx->p->device); delete ctx->p; delete ctx; }
     B200_CATCH
 }
 int b200_ctx_peer_export(b200_ctx* ctx, void* handle64)
@@ -92,6 +92,7 @@ int b200_ctx_mark(b200_ctx* ctx, int i)
 {
     B200_TRY
     B200_CHECK(i >= 0 && i < 4, "mark index");
+    B200_CUDA(cudaSetDevice(ctx->p->device));
     B200_CUDA(cudaEventRecord(ctx->p->marks[i], ctx->p->stream));
     B200_CATCH
 }
@@ -99,6 +100,7 @@ int b200_ctx_elapsed_ms(b200_ctx* ctx, int i, int j, double* ms)
 {
     B200_TRY
     B200_CHECK(i >= 0 && i < 4 && j >= 0 && j < 4, "mark index");
+    B200_CUDA(cudaSetDevice(ctx->p->device));
     B200_CUDA(cudaEventSynchronize(ctx->p->marks[j]));
     float t = 0;
     B200_CUDA(cudaEventElapsedTime(&t, ctx->p->marks[i], ctx->p->marks[j]));
@@ -108,6 +110,7 @@ int b200_ctx_elapsed_ms(b200_ctx* ctx, int i, int j, double* ms)
 int b200_profile_enable(b200_ctx* ctx, int on)
 {
     B200_TRY
+    B200_CUDA(cudaSetDevice(ctx->p->device));
     ctx->p->profRead(nullptr, nullptr);
     ctx->p->profOn = on != 0;
     B200_CATCH
@@ -118,6 +121,7 @@ int b200_profile_read(b200_ctx* ctx, double* ms, int64_t* counts, int n)
 {
     B200_TRY
     double m[PC_NCAT]; int64_t c[PC_NCAT];
+    B200_CUDA(cudaSetDevice(ctx->p->device));
     ctx->p->profRead(m, c);
     for (int i = 0; i < n && i < PC_NCAT; i++) { ms[i] = m[i]; counts[i] = c[i]; }
     B200_CATCH
