@@ -430,8 +430,11 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
     auto halfDone = [&](bool publish) {
         pDone += HS;
         if (publish) {          // back-pressure for the halo ring (RH steps deep): once per group is plenty
+            // A plain (volatile) store, no release: what it guards are this warp's ring READS of positions < pDone, and those have
+            // completed -- the chain consumed their values.  st.release here compiles to MEMBAR.ALL.CTA, which also waits for the
+            // publishing global stores of the whole group: ~450 cycles per group on the critical path of every tile.
             __syncwarp();
-            if (lane == 0) st_release_cta_u32(&compProg, (unsigned)pDone);
+            if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(&compProg)), "r"((unsigned)pDone) : "memory");
         }
     };
     // first half of group `grp` (operands in `cur`), prefetching the second half of the same slot

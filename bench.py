@@ -470,13 +470,23 @@ def e2e_run(args, g, abi, torch, dist, world, barrier, n_global):
     barrier()
     t0 = time.perf_counter()
     g.set_field_async(abi.FIELD_ALPHA_POWDER, hP); g.set_field_async(abi.FIELD_T, hT); g.set_field_async(abi.FIELD_ALPHA_SOLID, hA)
+    dbg = os.environ.get("B200_E2E_DEBUG") == "1"
     for i in range(e_steps):
+        ta = time.perf_counter()
         g.apply_staged()                       # the staged inputs become the step's fields (device-to-device)
         if i + 1 < e_steps:                    # next step's inputs start crossing now, under this step's kernels
             g.set_field_async(abi.FIELD_ALPHA_POWDER, hP); g.set_field_async(abi.FIELD_T, hT); g.set_field_async(abi.FIELD_ALPHA_SOLID, hA)
+        tb = time.perf_counter()
         g.step()
+        tc = time.perf_counter()
         g.get_field_async(abi.FIELD_T, oT[i & 1]); g.get_field_async(abi.FIELD_ALPHA_SOLID, oA[i & 1])
+        if dbg:
+            print(f"e2e step {i}: stage+upload calls {1e3 * (tb - ta):.1f} ms, step {1e3 * (tc - tb):.1f} ms, download calls {1e3 * (time.perf_counter() - tc):.1f} ms",
+                  file=sys.stderr, flush=True)
+    tw = time.perf_counter()
     g.transfers_wait()
+    if dbg:
+        print(f"e2e drain {1e3 * (time.perf_counter() - tw):.1f} ms", file=sys.stderr, flush=True)
     barrier()
     et = reduce_max(time.perf_counter() - t0)
     return {"value": n_global * e_steps / et, "unit": UNIT, "h2d_bytes_per_step": 3 * 8 * nl * world,
