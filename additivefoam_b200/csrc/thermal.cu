@@ -247,6 +247,8 @@ void ThermalCase::setFieldAsync(int f, const double* in)
     (void)field(f);
     ensureIo(f, false);
     B200_CUDA(cudaStreamWaitEvent(h2dStream, evInFree[f], 0));          // the previous staged value has been consumed (no-op the first time)
+    if (stageOut[f]) B200_CUDA(cudaStreamWaitEvent(h2dStream, evOutDone[f], 0));   // ... and an outstanding download of this field has landed:
+                                                                        // the round trip device -> host buffer -> device is ordered without the host
     B200_CUDA(cudaMemcpyAsync(stageIn[f], in, (size_t)dims.nCells() * sizeof(double), cudaMemcpyHostToDevice, h2dStream));
     B200_CUDA(cudaEventRecord(evIn[f], h2dStream));
     inPending[f] = true;
@@ -422,8 +424,13 @@ void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, 
     B200_LAUNCH_CHECK(); }
     haloExchange(kappa);
     haloExchange(rKappa);
+    // DiNum and the face coefficients of the coming assembly in one pass over the kappa stencil; which form of `upper` the step will
+    // want (thermoScheme.H:25-31 or :34-39) is only known after these reductions, so the form of the previous step is written and
+    // assembleBase() redoes the faces alone when the guess was wrong
     { ProfScope ps_(ctx, PC_DINUM);
-    k_dinum<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, geo, sidesDev, kappa, Cp, mat.rho, red);
+    if (lastExplicit) k_dinum_faces<true><<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, geo, sidesDev, kappa, rKappa, Cp, mat.rho, upper, red);
+    else k_dinum_faces<false><<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, geo, sidesDev, kappa, rKappa, Cp, mat.rho, upper, red);
+    upperForm = lastExplicit ? 2 : 1;
     B200_LAUNCH_CHECK(); }
     if (ctx->nranks > 1) {
         ctx->allreduceMax(red.result + R_ALPHACO, 1);
@@ -600,7 +607,8 @@ void ThermalCase::assembleBase(bool explicitSolve, double rDeltaT)
                                                                si.valueFraction, si.Tb, si.intCoeff, si.bouCoeff, 0, 1, si.n);
             B200_LAUNCH_CHECK();
         }
-        { ProfScope ps_(ctx, PC_FACES); k_faces<false><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
+        if (upperForm != 1) { ProfScope ps_(ctx, PC_FACES); k_faces<false><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
+        upperForm = 1; lastExplicit = false;
         // thermoScheme.H:34-39 fvm::ddt(T) with the scheme of fvSchemes
         BackwardCoeffs kT{rDeltaT, 1, 1, 0, false};
         if (backward()) kT = backwardCoeffs(TnOld);
@@ -609,7 +617,8 @@ void ThermalCase::assembleBase(bool explicitSolve, double rDeltaT)
     } else {
         touchOldTimes(true, 1);            // thermoScheme.H:25-31: the explicit form always uses EulerDdtScheme
         haloExchange(T);
-        { ProfScope ps_(ctx, PC_FACES); k_faces<true><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
+        if (upperForm != 2) { ProfScope ps_(ctx, PC_FACES); k_faces<true><<<grid, BLK, 0, s>>>(dims, geo, rKappa, upper); B200_LAUNCH_CHECK(); }
+        upperForm = 2; lastExplicit = true;
         { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_explicit<<<grid, BLK, 0, s>>>(dims, geo, sidesDev, Cp, Told, T, qDot, upper, rKappa, diag0, source0, rDeltaT, mat.rho);
         B200_LAUNCH_CHECK(); }
     }

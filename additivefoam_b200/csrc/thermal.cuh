@@ -117,6 +117,8 @@ private:
            *diag0 = nullptr, *source0 = nullptr, *diag = nullptr, *source = nullptr, *upper = nullptr, *wbuf = nullptr,
            *Toldold = nullptr, *alpha1oldold = nullptr;
     size_t wbufCap = 0;
+    int upperForm = 0;                   // what `upper` holds: 0 nothing valid, 1 the implicit off-diagonals, 2 the harmonic face conductivities
+    bool lastExplicit = false;           // form the previous step assembled (the guess k_dinum_faces writes)
     double* d_thermo = nullptr;          // thermoPath table on the device: x then y
     std::unique_ptr<Ldu> ldu;
     RedWork red{};

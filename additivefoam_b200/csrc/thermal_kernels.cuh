@@ -140,6 +140,54 @@ __global__ void __launch_bounds__(BLK) k_faces(BlockDims d, Geom g, const double
     }
 }
 
+// k_dinum and k_faces in one pass over the kappa stencil (both run between updateProperties.H and the assembly, and both are
+// functions of kappa alone): the six neighbour values are loaded once, unconditionally (clamped to the cell itself at the block's
+// edge), the DiNum sum and the three upper coefficients follow with the very expressions of the two kernels above.
+template <bool EXPLICIT>
+__global__ void __launch_bounds__(BLK) k_dinum_faces(BlockDims d, Geom g, SidesDev sd, const double* __restrict__ kappa,
+                                                     const double* __restrict__ rKappa, const double* __restrict__ Cp, double rho,
+                                                     double* __restrict__ upper, RedWork red)
+{
+    const int nx = d.nx; const int64_t nxny = (int64_t)d.nx * d.ny;
+    double mx = -1e300;
+    B200_FOR_CELLS(d)
+    {
+        B200_CELL_INDEX(d)
+        const RowCtx r = row_ctx(d, row);
+        int fzl, fyl, fxl, fx, fy, fz;
+        cell_faces(d, r, i, fzl, fyl, fxl, fx, fy, fz);
+        const double* kp = kappa + c; const double* rp = rKappa + c;
+        const double kc = ld_first(kp), cp = ld_first(Cp + c);
+        const double kzl = ld_first(fzl >= 0 ? kp - nxny : kp), kyl = ld_first(fyl >= 0 ? kp - nx : kp), kxl = ld_first(fxl >= 0 ? kp - 1 : kp);
+        const double kx = ld_first(fx >= 0 ? kp + 1 : kp), ky = ld_first(fy >= 0 ? kp + nx : kp), kz = ld_first(fz >= 0 ? kp + nxny : kp);
+        const double rP = ld_first(rp), rX = ld_first(fx >= 0 ? rp + 1 : rp), rY = ld_first(fy >= 0 ? rp + nx : rp),
+                     rZ = ld_first(fz >= 0 ? rp + nxny : rp);
+        double S = 0.0;
+        if (fzl >= 0) S += g.sfz * (0.5 * (kzl - kc) + kc) * g.dcz;
+        if (fyl >= 0) S += g.sfy * (0.5 * (kyl - kc) + kc) * g.dcy;
+        if (fxl >= 0) S += g.sfx * (0.5 * (kxl - kc) + kc) * g.dcx;
+        if (fx >= 0) S += g.sfx * (0.5 * (kc - kx) + kx) * g.dcx;
+        if (fy >= 0) S += g.sfy * (0.5 * (kc - ky) + ky) * g.dcy;
+        if (fz >= 0) S += g.sfz * (0.5 * (kc - kz) + kz) * g.dcz;
+        const bool bnd = i == 0 || i == nx - 1 || j == 0 || j == d.ny - 1 || k == 0 || k == d.nz - 1;
+        for (int q = 0; bnd && q < sd.nOrder; q++) {
+            const int s = sd.order[q];
+            if (!on_side(d, s, i, j, k)) continue;
+            if (sd.type[s] == SIDE_PROCESSOR) {
+                const double kn = kappa[s == B200_ZMIN ? c - nxny : c + nxny];
+                S += g.sfz * (0.5 * kc + (1.0 - 0.5) * kn) * g.dcz;
+            } else S += side_area(g, s) * kc * side_delta(g, s);
+        }
+        mx = fmax(mx, S / (g.V * rho * cp));
+        if (fx >= 0) { const double kf = 1.0 / (0.5 * (rP - rX) + rX); upper[fx] = EXPLICIT ? kf : 0.0 - g.dcx * (kf * g.sfx); }
+        if (fy >= 0) { const double kf = 1.0 / (0.5 * (rP - rY) + rY); upper[fy] = EXPLICIT ? kf : 0.0 - g.dcy * (kf * g.sfy); }
+        if (fz >= 0) { const double kf = 1.0 / (0.5 * (rP - rZ) + rZ); upper[fz] = EXPLICIT ? kf : 0.0 - g.dcz * (kf * g.sfz); }
+    }
+    __shared__ double smem[32];
+    double v[1] = {mx}; const int ops[1] = {1};
+    grid_reduce<1>(v, ops, red, R_DIMAX, smem);
+}
+
 // One thread per face of one block side: mixedTemperature updateCoeffs
 // (mixedTemperatureFvPatchScalarField.C:157-188) and, for the implicit form, the boundary coefficients of
 // -fvm::laplacian(kappa, T) ([UPSTREAM] gaussLaplacianScheme + mixed/fixedValue/processor gradient coeffs).

@@ -295,7 +295,10 @@ int  b200_case_reset_alpha_solid(b200_case* c);
  *   get_field_async : snapshot of the field, then device -> host on a second copy stream; returns at once.
  *   transfers_wait  : both copy streams and the compute stream have drained; the host buffers hold the snapshots.
  * Typical loop: set_field_async(inputs of step 0); for n: apply_staged; set_field_async(inputs of step n+1); step;
- * get_field_async(results of step n).  The copies of step n+1 / step n then run under the kernels of step n / n+1. */
+ * get_field_async(results of step n).  The copies of step n+1 / step n then run under the kernels of step n / n+1.
+ * An upload of a field is ordered after the outstanding download of the same field of the same case, so "results to the host buffer,
+ * the host buffer back as the next inputs" can be queued without a host wait in between: two cases sharing one GPU then hide each
+ * other's PCIe traffic -- get_field_async(B), set_field_async(B), step(A), apply_staged(B); the same for A under step(B). */
 int  b200_case_set_field_async(b200_case* c, int32_t field, const double* pinnedIn);
 int  b200_case_apply_staged(b200_case* c);
 int  b200_case_get_field_async(b200_case* c, int32_t field, double* pinnedOut);
