@@ -4,6 +4,7 @@ another build is never reported.
 Usage: python tools/summarize_ncu.py <cells per GPU> <launches.csv> <full.ncu-rep> [more.ncu-rep ...]     (prefix: env PREFIX, default r2)"""
 import collections
 import csv
+import re
 import subprocess
 import sys
 
@@ -44,7 +45,8 @@ with open(f"profiles/{PREFIX}_top_kernels_ncu_full_{cells}.csv", "w") as f:
     w.writerow(["kernel", "duration_ms", "dram_read_bytes", "dram_write_bytes", "dram_throughput_pct_of_peak", "registers_per_thread",
                 "warps_active_pct", "grid", "block"])
     for rep in reps:
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        # a capture exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`), or the .ncu-rep itself
+        out = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(out.splitlines()))
         hdr, units = rows[0], rows[1]
         col = {n: i for i, n in enumerate(hdr)}
@@ -60,9 +62,10 @@ print(open(f"profiles/{PREFIX}_top_kernels_ncu_full_{cells}.csv").read())
 
 # ---- per-launch DRAM traffic of the kernels bench.py's roofline can name, for THIS build
 def group_of(k):
-    for pat, g in (("k_wave2<(int)2", "sweep_bwd"), ("k_wave4<(int)2", "sweep_bwd"), ("k_wave3<(int)2", "sweep_bwd"), ("k_wave2<(int)1", "sweep_fwd"),
-                   ("k_wave4<(int)1", "sweep_fwd"), ("k_wave3<(int)1", "sweep_fwd"), ("k_wave2<(int)0", "factor"), ("k_wave4<(int)0", "factor"),
-                   ("k_amul_block", "amul"), ("k_corrector", "corrector"), ("k_assemble_implicit", "assemble"), ("k_props", "props"),
+    m = re.search(r"k_wave[234]<(?:\(int\))?([012])\b", k)        # first template argument: 0 factor, 1 forward, 2 backward sweep
+    if m:
+        return ("factor", "sweep_fwd", "sweep_bwd")[int(m.group(1))]
+    for pat, g in (("k_amul_block", "amul"), ("k_corrector", "corrector"), ("k_assemble_implicit", "assemble"), ("k_props", "props"),
                    ("k_dinum", "dinum"), ("k_faces", "faces"), ("k_alpha_update", "alpha"), ("k_normfactor_block", "normfactor")):
         if pat in k:
             return g
