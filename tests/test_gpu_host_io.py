@@ -59,7 +59,7 @@ def test_two_cases_alternating_through_host_buffers(ctx, oracle):
             g.set_field_async(f, h[f])
 
     nsteps = [0, 0]
-    for i in range(24):
+    for i in range(60):
         x, y = i & 1, 1 - (i & 1)
         if i > 0:
             out_and_back(y)
@@ -75,7 +75,7 @@ def test_two_cases_alternating_through_host_buffers(ctx, oracle):
         assert np.array_equal(Th, Tr), q
         assert np.array_equal(through_host[q].field(abi.FIELD_ALPHA_SOLID), resident[q].field(abi.FIELD_ALPHA_SOLID)), q
         assert float(np.max(np.abs(Th - To)) / np.max(np.abs(To))) < 1e-9
-        assert To.max() > 1000.0
+        assert To.max() > 400.0
     # case 0 was downloaded after its last step (during case 1's): its host buffer holds its final T
     assert np.array_equal(host[0][abi.FIELD_T], through_host[0].field(abi.FIELD_T))
     for g in through_host + resident:
