@@ -15,8 +15,8 @@ SUPER_GAUSSIAN, MODIFIED_SUPER_GAUSSIAN, PROJECTED_GAUSSIAN = 0, 1, 2
 ABSORPTION_CONSTANT, ABSORPTION_KELLY = 0, 1
 KELLY_CONE, KELLY_CYLINDER = 0, 1
 FIELD_T, FIELD_ALPHA_SOLID, FIELD_ALPHA_POWDER, FIELD_KAPPA, FIELD_CP, FIELD_QDOT, FIELD_DFDT, FIELD_T0, FIELD_T_OLD, FIELD_ALPHA_SOLID_OLD, \
-    FIELD_T_OLD_OLD, FIELD_ALPHA_SOLID_OLD_OLD = range(12)
-DDT_EULER, DDT_BACKWARD = 0, 1
+    FIELD_T_OLD_OLD, FIELD_ALPHA_SOLID_OLD_OLD, FIELD_DDT0_T, FIELD_DDT0_ALPHA_SOLID = range(14)
+DDT_EULER, DDT_BACKWARD, DDT_CRANK_NICOLSON = 0, 1, 2
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)
@@ -57,7 +57,7 @@ class Controls(C.Structure):
                 ("explicitSolve", C.c_int32),
                 ("solver", C.c_int32), ("preconditioner", C.c_int32),
                 ("tolerance", C.c_double), ("relTol", C.c_double), ("minIter", C.c_int32), ("maxIter", C.c_int32),
-                ("ddtScheme", C.c_int32)]
+                ("ddtScheme", C.c_int32), ("ocCoeff", C.c_double)]
 
 
 class CaseDesc(C.Structure):

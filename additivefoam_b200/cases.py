@@ -64,7 +64,7 @@ def default_controls(**kw):
     c = dict(startTime=0.0, endTime=0.004, deltaT=1e-7, adjustTimeStep=1, maxCo=0.5, maxDi=1.0, maxAlphaCo=1.0,
              maxDeltaT=1e15, writeInterval=0.001, nThermoCorrectors=20, thermoTolerance=1e-8, Tmax=0.0,
              explicitSolve=1, solver=abi.SOLVER_PBICGSTAB, preconditioner=abi.PRECOND_DILU, tolerance=1e-15,
-             relTol=0.0, minIter=1, maxIter=20, ddtScheme=abi.DDT_EULER)
+             relTol=0.0, minIter=1, maxIter=20, ddtScheme=abi.DDT_EULER, ocCoeff=1.0)
     c.update(kw)
     return c
 

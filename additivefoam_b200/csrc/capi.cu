@@ -26,7 +26,7 @@ static thread_local std::string g_err;
 extern "C" {
 
 const char* b200_last_error(void) { return g_err.c_str(); }
-int b200_abi_version(void) { return 2; }       // 2: b200_controls.ddtScheme
+int b200_abi_version(void) { return 3; }       // 2: b200_controls.ddtScheme; 3: b200_controls.ocCoeff (CrankNicolson)
 
 int b200_nccl_unique_id(void* out128)
 {

@@ -137,8 +137,10 @@ ThermalCase::ThermalCase(Ctx* c, const b200_case_desc& desc) : ctx(c)
         if (cz > desc.powderZMin) { k_fill<<<flat_grid(ctx, (int64_t)plane), BLK, 0, s>>>((int64_t)plane, alpha3 + (size_t)k * plane, 1.0); B200_LAUNCH_CHECK(); }
     }
     time_ = ctl.startTime; deltaT_ = ctl.deltaT; deltaT0_ = deltaT_; deltaTSave_ = deltaT_;
-    B200_CHECK(ctl.ddtScheme == B200_DDT_EULER || ctl.ddtScheme == B200_DDT_BACKWARD, "ddtScheme: Euler and backward are implemented (CrankNicolson is not)");
-    if (backward()) {
+    B200_CHECK(ctl.ddtScheme == B200_DDT_EULER || ctl.ddtScheme == B200_DDT_BACKWARD || ctl.ddtScheme == B200_DDT_CRANK_NICOLSON,
+               "ddtScheme: Euler, backward or CrankNicolson (thermoScheme.H:4-15)");
+    B200_CHECK(!crankNicolson() || (ctl.ocCoeff >= 0.0 && ctl.ocCoeff <= 1.0), "CrankNicolson: ocCoeff must lie in [0, 1]");
+    if (backward() || crankNicolson()) {
         Toldold = allocField(); alpha1oldold = allocField();
         k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, Toldold, Tinitial); B200_LAUNCH_CHECK();
         k_fill<<<flat_grid(ctx, n), BLK, 0, s>>>(n, alpha1oldold, a0); B200_LAUNCH_CHECK();
@@ -185,8 +187,14 @@ double* ThermalCase::field(int f)
     case B200_FIELD_T0: return T0;
     case B200_FIELD_T_OLD: return Told;
     case B200_FIELD_ALPHA_SOLID_OLD: return alpha1old;
-    case B200_FIELD_T_OLD_OLD: B200_CHECK(Toldold != nullptr, "the second old-time level exists only with ddtScheme backward"); return Toldold;
-    case B200_FIELD_ALPHA_SOLID_OLD_OLD: B200_CHECK(alpha1oldold != nullptr, "the second old-time level exists only with ddtScheme backward"); return alpha1oldold;
+    case B200_FIELD_T_OLD_OLD: B200_CHECK(Toldold != nullptr, "the second old-time level exists only with ddtScheme backward or CrankNicolson"); return Toldold;
+    case B200_FIELD_ALPHA_SOLID_OLD_OLD: B200_CHECK(alpha1oldold != nullptr, "the second old-time level exists only with ddtScheme backward or CrankNicolson"); return alpha1oldold;
+    case B200_FIELD_DDT0_T: case B200_FIELD_DDT0_ALPHA_SOLID: {
+        B200_CHECK(crankNicolson(), "ddt0 exists only with ddtScheme CrankNicolson");
+        double*& d0 = f == B200_FIELD_DDT0_T ? ddt0T : ddt0A;
+        if (!d0) d0 = allocField();                       // zero, as the scheme would create it
+        return d0;
+    }
     }
     throw Error("unknown field id");
 }
@@ -406,6 +414,32 @@ void ThermalCase::touchOldTimes(bool ofT, int levels)
     nOld = std::max(nOld, levels);
 }
 
+// [UPSTREAM] CrankNicolsonDdtScheme::fvcDdt / fvmDdt up to the use of ddt0 (the rules: oracle/af_thermal.hpp, Case::cnPrepare)
+CnCoeffs ThermalCase::cnPrepare(bool ofT, bool fvm)
+{
+    Ddt0State& st = ofT ? ddt0StateT : ddt0StateA;
+    double*& d0 = ofT ? ddt0T : ddt0A;
+    if (!st.exists) {
+        if (!d0) d0 = allocField();
+        else B200_CUDA(cudaMemsetAsync(d0, 0, (size_t)dims.nCells() * sizeof(double), ctx->stream));
+        st.exists = true; st.startTimeIndex = timeIndex; st.timeIndex = timeIndex;
+    }
+    const double psi = ctl.ocCoeff;
+    CnCoeffs k;
+    k.rDtCoef = (timeIndex > st.startTimeIndex ? 1 + psi : 1) / deltaT_;
+    k.psi = psi; k.ddt0 = d0; k.on = true;
+    touchOldTimes(ofT, fvm ? 2 : 1);
+    if (st.timeIndex != timeIndex) {
+        touchOldTimes(ofT, 2);
+        const double rDtCoef0 = (timeIndex > st.startTimeIndex + 1 ? 1 + psi : 1) / deltaT0_;
+        const int64_t n = (int64_t)dims.nCells();
+        k_ddt0_update<<<flat_grid(ctx, n), BLK, 0, ctx->stream>>>(n, d0, ofT ? Told : alpha1old, ofT ? Toldold : alpha1oldold, rDtCoef0, k);
+        B200_LAUNCH_CHECK();
+    }
+    st.timeIndex = timeIndex;
+    return k;
+}
+
 // updateProperties.H + the two numbers of setDeltaT.H (alphaCoNum without dt history issues, DiNum/dt)
 void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, double& minAlpha1, bool propertiesOnly)
 {
@@ -415,12 +449,14 @@ void ThermalCase::updatePropertiesAndNumbers(double& alphaCoMax, double& diMax, 
     m.rho = mat.rho; m.Lf = mat.Lf; m.Tliq = Tliq; m.Tsol = Tsol;
     // setDeltaT.H:6-11 evaluates fvc::ddt(T) with the scheme of fvSchemes (only when adjustTimeStep: the levels are created there)
     BackwardCoeffs kb{1.0 / deltaT_, 1, 1, 0, false};
+    CnCoeffs kc{0, 1, nullptr, false};
     if (!propertiesOnly) {             // (createFields.H:112 runs updateProperties.H alone: no fvc::ddt(T), no old-time level is created)
-        if (backward() && ctl.adjustTimeStep) { kb = backwardCoeffs(TnOld); touchOldTimes(true, 2); }
+        if (crankNicolson() && ctl.adjustTimeStep) kc = cnPrepare(true, false);
+        else if (backward() && ctl.adjustTimeStep) { kb = backwardCoeffs(TnOld); touchOldTimes(true, 2); }
         else if (ctl.adjustTimeStep) touchOldTimes(true, 1);
     }
     { ProfScope ps_(ctx, PC_PROPS);
-    k_props<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, m, T, Told, alpha1, alpha3, kappa, rKappa, Cp, 1.0 / deltaT_, deltaT_, red, kb, Toldold);
+    k_props<<<cells_grid(ctx, dims), BLK, 0, s>>>(dims, m, T, Told, alpha1, alpha3, kappa, rKappa, Cp, 1.0 / deltaT_, deltaT_, red, kb, Toldold, kc);
     B200_LAUNCH_CHECK(); }
     haloExchange(kappa);
     haloExchange(rKappa);
@@ -611,9 +647,11 @@ void ThermalCase::assembleBase(bool explicitSolve, double rDeltaT)
         upperForm = 1; lastExplicit = false;
         // thermoScheme.H:34-39 fvm::ddt(T) with the scheme of fvSchemes
         BackwardCoeffs kT{rDeltaT, 1, 1, 0, false};
+        CnCoeffs kc{0, 1, nullptr, false};
         if (backward()) kT = backwardCoeffs(TnOld);
-        touchOldTimes(true, backward() ? 2 : 1);
-        { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho, kT, Toldold); B200_LAUNCH_CHECK(); }
+        if (crankNicolson()) kc = cnPrepare(true, true);
+        else touchOldTimes(true, backward() ? 2 : 1);
+        { ProfScope ps_(ctx, PC_ASSEMBLE); k_assemble_implicit<<<grid, BLK, 0, s>>>(dims, geo, Cp, Told, qDot, upper, diag0, source0, rDeltaT, mat.rho, kT, Toldold, kc); B200_LAUNCH_CHECK(); }
     } else {
         touchOldTimes(true, 1);            // thermoScheme.H:25-31: the explicit form always uses EulerDdtScheme
         haloExchange(T);
@@ -664,12 +702,13 @@ void ThermalCase::step(b200_step_report* rep)
     // thermoScheme.H:41-68: the rDeltaT of the Sp terms is scaled by coefft = 1 + deltaT/(deltaT + deltaT0) -- runTime.deltaT0() itself,
     // not the scheme's guarded one -- in the implicit form of the backward scheme
     const bool bwd = backward() && !explicitSolve;
-    const double rDeltaTSp = bwd ? rDeltaT * (1.0 + deltaT_ / (deltaT_ + deltaT0_)) : rDeltaT;
+    const bool cn = crankNicolson() && !explicitSolve;       // (:51-65: coefft = 1 + ocCoeff, at every step)
+    const double rDeltaTSp = bwd ? rDeltaT * (1.0 + deltaT_ / (deltaT_ + deltaT0_)) : cn ? rDeltaT * (1.0 + ctl.ocCoeff) : rDeltaT;
     CorrectorArgs ca;
     ca.alpha1old = alpha1old; ca.diag0 = diag0; ca.source0 = source0; ca.T = T; ca.alpha1 = alpha1; ca.dFdT = dFdT; ca.T0 = T0;
     ca.diag = diag; ca.source = source; ca.thermo = d_thermo; ca.nThermo = mat.nThermo; ca.Tliq = Tliq; ca.Tsol = Tsol;
     ca.thermoTol = ctl.thermoTolerance; ca.Tmax = ctl.Tmax > 0 ? ctl.Tmax : kVGreat; ca.rDeltaT = rDeltaTSp; ca.rDeltaTEuler = rDeltaT;
-    ca.kA = BackwardCoeffs{rDeltaT, 1, 1, 0, false}; ca.alpha1oldold = alpha1oldold;
+    ca.kA = BackwardCoeffs{rDeltaT, 1, 1, 0, false}; ca.alpha1oldold = alpha1oldold; ca.cnA = CnCoeffs{0, 1, nullptr, false};
     ca.rho = mat.rho; ca.Lf = mat.Lf;
     const size_t shm = 2 * (size_t)mat.nThermo * sizeof(double);
     const int grid = cells_grid(ctx, dims);
@@ -684,7 +723,8 @@ void ThermalCase::step(b200_step_report* rep)
     for (int tCorr = 0; tCorr < nThermoCorr; tCorr++) {
         // TEqn.H:36-39: fvc::ddt(alpha1) with the scheme (guarded by the levels alpha.solid has at THIS call), Euler in the explicit form
         if (bwd) ca.kA = backwardCoeffs(a1nOld);
-        touchOldTimes(false, bwd ? 2 : 1);
+        if (cn) ca.cnA = cnPrepare(false, false);
+        else touchOldTimes(false, bwd ? 2 : 1);
         if (explicitSolve) {
             { ProfScope ps_(ctx, PC_CORRECTOR); k_corrector<true><<<grid, BLK, shm, s>>>(dims, geo, sidesDev, ca, red); B200_LAUNCH_CHECK(); }
             perf = SolvePerf(); perf.converged = 1;

@@ -60,6 +60,10 @@ struct BoxRange { int i0, i1, j0, j1, k0, k1; };   // half-open local index box
 // [UPSTREAM] backwardDdtScheme coefficients: coefft = 1 + dt/(dt + dt0), coefft00 = dt*dt/(dt0*(dt + dt0)), coefft0 = coefft + coefft00.
 // Euler is {1/dt, 1, 1, 0} with `on` false (the kernels then keep the Euler expressions, operation for operation).
 struct BackwardCoeffs { double rDeltaT, coefft, coefft0, coefft00; bool on; };
+// [UPSTREAM] CrankNicolsonDdtScheme as one call of fvcDdt / fvmDdt needs it: rDtCoef_ = coef_/deltaT, psi = ocCoeff(), the scheme's
+// ddt0 field (already brought to this time index).  offCentre_(ddt0) = psi < 1 ? psi*ddt0 : ddt0.
+struct CnCoeffs { double rDtCoef, psi; const double* ddt0; bool on; };
+__host__ __device__ inline double cn_off_centre(const CnCoeffs& k, double ddt0) { return k.psi < 1 ? k.psi * ddt0 : ddt0; }
 
 class ThermalCase {
 public:
@@ -106,6 +110,14 @@ private:
     int TnOld = 0, a1nOld = 0;
     bool backward() const { return ctl.ddtScheme == B200_DDT_BACKWARD; }
     BackwardCoeffs backwardCoeffs(int nOld) const;
+    // ddtScheme CrankNicolson (thermoScheme.H:51-65; the scheme itself is [UPSTREAM] CrankNicolsonDdtScheme, restated in
+    // oracle/af_thermal.hpp where its rules are written out): per field ddt0, created zero at its first use, the time index of that
+    // moment and the time index it was last brought to
+    struct Ddt0State { bool exists = false; int startTimeIndex = 0, timeIndex = 0; };
+    Ddt0State ddt0StateT, ddt0StateA;
+    double *ddt0T = nullptr, *ddt0A = nullptr;
+    bool crankNicolson() const { return ctl.ddtScheme == B200_DDT_CRANK_NICOLSON; }
+    CnCoeffs cnPrepare(bool ofT, bool fvm);       // everything one fvcDdt / fvmDdt does before it uses ddt0
     void touchOldTimes(bool ofT, int levels);
     int timeIndex = 0, writeTimeIndex = 0;
     double alphaCoNum = 0, DiNum = 0;
@@ -136,7 +148,7 @@ private:
     void solidificationExecute();
 
     // streamed host I/O: two copy streams beside the compute stream, one staging buffer per field and direction
-    static constexpr int NIOF = 12;
+    static constexpr int NIOF = 14;
     cudaStream_t h2dStream = nullptr, d2hStream = nullptr;
     double* stageIn[NIOF] = {nullptr}; double* stageOut[NIOF] = {nullptr};
     cudaEvent_t evIn[NIOF] = {nullptr}, evInFree[NIOF] = {nullptr}, evOutReady[NIOF] = {nullptr}, evOutDone[NIOF] = {nullptr};

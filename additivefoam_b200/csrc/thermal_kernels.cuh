@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(BLK) k_props(BlockDims d, MatDev m, const doub
                                                const double* __restrict__ alpha1, double* __restrict__ alpha3, double* __restrict__ kappa,
                                                double* __restrict__ rKappa, double* __restrict__ Cp, double rDeltaT, double deltaT,
                                                RedWork red, BackwardCoeffs kb = BackwardCoeffs{0, 1, 1, 0, false},
-                                               const double* __restrict__ Toldold = nullptr)
+                                               const double* __restrict__ Toldold = nullptr, CnCoeffs kc = CnCoeffs{0, 1, nullptr, false})
 {
     double mxA = -1e300, mnA1 = 1e300;
     B200_FOR_CELLS(d)
@@ -75,7 +75,9 @@ __global__ void __launch_bounds__(BLK) k_props(BlockDims d, MatDev m, const doub
         const double cp = (1.0 - a3) * (a1 * poly3(m.Cp[0], T1) + a2 * poly3(m.Cp[1], T2)) + a3 * poly3(m.Cp[2], T1);
         kappa[c] = kap; rKappa[c] = 1.0 / kap; Cp[c] = cp;
         // setDeltaT.H:6-11 fvc::ddt(T): Euler, or backward rDeltaT*(coefft*T - coefft0*T.oldTime() + coefft00*T.oldTime().oldTime())
-        const double ddtT = kb.on ? kb.rDeltaT * (kb.coefft * Tc - kb.coefft0 * Told[c] + kb.coefft00 * Toldold[c]) : rDeltaT * (Tc - Told[c]);
+        // ... or CrankNicolson rDtCoef*(T - T.oldTime()) - offCentre(ddt0(T))
+        const double ddtT = kc.on ? kc.rDtCoef * (Tc - Told[c]) - cn_off_centre(kc, kc.ddt0[c])
+                          : kb.on ? kb.rDeltaT * (kb.coefft * Tc - kb.coefft0 * Told[c] + kb.coefft00 * Toldold[c]) : rDeltaT * (Tc - Told[c]);
         mxA = fmax(mxA, fabs(ddtT) / (m.Tliq - m.Tsol) * deltaT);
         mnA1 = fmin(mnA1, a1);
     }
@@ -250,7 +252,8 @@ __global__ void k_side_evaluate(BlockDims d, int s, int type, double fixedValue,
 __global__ void __launch_bounds__(BLK) k_assemble_implicit(BlockDims d, Geom g, const double* __restrict__ Cp, const double* __restrict__ Told,
                                                            const double* __restrict__ qDot, const double* __restrict__ upper,
                                                            double* __restrict__ diag0, double* __restrict__ source0, double rDeltaT, double rho,
-                                                           BackwardCoeffs kb = BackwardCoeffs{0, 1, 1, 0, false}, const double* __restrict__ Toldold = nullptr)
+                                                           BackwardCoeffs kb = BackwardCoeffs{0, 1, 1, 0, false}, const double* __restrict__ Toldold = nullptr,
+                                                           CnCoeffs kc = CnCoeffs{0, 1, nullptr, false})
 {
     B200_FOR_CELLS(d)
     {
@@ -268,7 +271,10 @@ __global__ void __launch_bounds__(BLK) k_assemble_implicit(BlockDims d, Geom g, 
         if (fx >= 0) ld += upper[fx];
         if (fy >= 0) ld += upper[fy];
         if (fz >= 0) ld += upper[fz];
-        if (kb.on) {    // [UPSTREAM] backwardDdtScheme::fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*old - coefft00*oldOld)
+        if (kc.on) {    // [UPSTREAM] CrankNicolsonDdtScheme::fvmDdt: diag = rDtCoef*V, source = (rDtCoef*old + offCentre(ddt0))*V
+            diag0[c] = (kc.rDtCoef * g.V) * rhoCp - ld;
+            source0[c] = ((kc.rDtCoef * Told[c] + cn_off_centre(kc, kc.ddt0[c])) * g.V) * rhoCp + g.V * qDot[c];
+        } else if (kb.on) {    // [UPSTREAM] backwardDdtScheme::fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*old - coefft00*oldOld)
             diag0[c] = ((kb.coefft * kb.rDeltaT) * g.V) * rhoCp - ld;
             source0[c] = (kb.rDeltaT * g.V * (kb.coefft0 * Told[c] - kb.coefft00 * Toldold[c])) * rhoCp + g.V * qDot[c];
         } else {
@@ -336,6 +342,7 @@ struct CorrectorArgs {
     double Tliq, Tsol, thermoTol, Tmax, rDeltaT, rDeltaTEuler, rho, Lf;
     BackwardCoeffs kA;              // fvc::ddt(alpha1) of TEqn.H:36-39 when the scheme is backward (kA.on), else the Euler form
     const double* alpha1oldold;
+    CnCoeffs cnA;                   // ... or CrankNicolson (cnA.on)
 };
 
 template <bool EXPLICIT>
@@ -370,7 +377,8 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         const double source1 = (g.V * (Acoef * a.Tmax)) * a.rDeltaT;
         const double diag2 = (g.V * dF) * s2;
         const double source2 = (g.V * (dF * t0)) * s2;
-        const double su = a.kA.on ? (a.rho * a.Lf) * (a.kA.rDeltaT * (a.kA.coefft * y - a.kA.coefft0 * aold + a.kA.coefft00 * aoo))
+        const double su = a.cnA.on ? (a.rho * a.Lf) * (a.cnA.rDtCoef * (y - aold) - cn_off_centre(a.cnA, a.cnA.ddt0[c]))
+                        : a.kA.on ? (a.rho * a.Lf) * (a.kA.rDeltaT * (a.kA.coefft * y - a.kA.coefft0 * aold + a.kA.coefft00 * aoo))
                                   : (a.rho * a.Lf) * (a.rDeltaTEuler * (y - aold));
         const double sourceR = source2 - g.V * su;
         double dg = (d0 + diag1) - diag2;
@@ -415,6 +423,14 @@ __global__ void __launch_bounds__(BLK) k_corrector(BlockDims d, Geom g, SidesDev
         double v[1] = {mxRes}; const int ops[1] = {1};
         grid_reduce<1>(v, ops, red, R_RESID, smem);
     }
+}
+
+// [UPSTREAM] CrankNicolsonDdtScheme, evaluate(ddt0): ddt0 = rDtCoef0*(vf.oldTime() - vf.oldTime().oldTime()) - offCentre(ddt0)
+__global__ void __launch_bounds__(BLK) k_ddt0_update(int64_t n, double* __restrict__ ddt0, const double* __restrict__ old,
+                                                     const double* __restrict__ oldold, double rDtCoef0, CnCoeffs k)
+{
+    for (int64_t c = blockIdx.x * (int64_t)BLK + threadIdx.x; c < n; c += (int64_t)gridDim.x * BLK)
+        ddt0[c] = rDtCoef0 * (old[c] - oldold[c]) - cn_off_centre(k, ddt0[c]);
 }
 
 // TEqn.H:46-53: alpha1 = min(max(alpha10 + dFdT*(T - T0), 0), 1); residual = max|alpha1 - alpha10|

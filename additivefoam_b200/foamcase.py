@@ -345,7 +345,7 @@ def _read_controls(case_dir):
     if int(pimple.get("nOuterCorrectors", 0)) > 0:
         raise FoamCaseError("PIMPLE nOuterCorrectors > 0 asks for the pU loop and fvm::div(phi,T) with phi != 0, which the library "
                             "does not implement (thermal path only)")
-    ddt_scheme = _check_schemes(case_dir)
+    ddt_scheme, oc_coeff = _check_schemes(case_dir)
     adjustable = c.get("writeControl") == "adjustableRunTime"
     return dict(startTime=float(c.get("startTime", 0.0)), endTime=float(c["endTime"]), deltaT=float(c["deltaT"]),
                 adjustTimeStep=_switch(c["adjustTimeStep"], "adjustTimeStep") if "adjustTimeStep" in c else 0,
@@ -356,7 +356,7 @@ def _read_controls(case_dir):
                 explicitSolve=_switch(pimple["explicitSolve"], "explicitSolve") if "explicitSolve" in pimple else 0,
                 solver=_SOLVERS[ts["solver"]], preconditioner=_PRECONDS[precond], tolerance=float(ts.get("tolerance", 1e-6)),
                 relTol=float(ts.get("relTol", 0.0)), minIter=int(ts.get("minIter", 0)), maxIter=int(ts.get("maxIter", 1000)),
-                ddtScheme=ddt_scheme)
+                ddtScheme=ddt_scheme, ocCoeff=oc_coeff)
 
 
 def _scheme(d, section, *keys):
@@ -370,17 +370,31 @@ def _scheme(d, section, *keys):
 
 
 def _check_schemes(case_dir):
-    """The kernels hard-code the schemes every shipped case selects (tutorials/*/system/fvSchemes:18-47): Euler or backward ddt
-    (thermoScheme.H:41-49), Gauss harmonic for laplacian(kappa,T), linear interpolation (setDeltaT.H:21-27).  Anything else is
-    refused instead of being approximated."""
+    """The kernels hard-code the schemes every shipped case selects (tutorials/*/system/fvSchemes:18-47): Euler, backward or
+    CrankNicolson ddt (thermoScheme.H:2-15,41-65), Gauss harmonic for laplacian(kappa,T), linear interpolation (setDeltaT.H:21-27).
+    Anything else is refused instead of being approximated.  Returns (ddtScheme, ocCoeff)."""
     path = os.path.join(case_dir, "system", "fvSchemes")
     if not os.path.exists(path):
         raise FoamCaseError("system/fvSchemes is missing")
     d = parse_dictionary(_read(case_dir, "system", "fvSchemes"))
     # thermoScheme.H:2 looks the scheme up by the field's name: mesh.schemes().ddt("T") -> the entry `T` if there is one, else `default`
     ddt = _scheme(d, "ddtSchemes", "T")
-    if ddt not in ("Euler", "backward"):
-        raise FoamCaseError(f"ddtSchemes {ddt!r}: Euler and backward are implemented (thermoScheme.H:41-49); CrankNicolson is not")
+    words = (ddt or "").split()
+    if not words or words[0] not in ("Euler", "backward", "CrankNicolson"):
+        raise FoamCaseError(f"ddtSchemes {ddt!r}: thermoScheme.H:4-15 accepts Euler, CrankNicolson or backward")
+    oc_coeff = 1.0
+    if words[0] == "CrankNicolson":
+        # thermoScheme.H:53-64 builds the scheme a second time from mesh.schemes().ddt("CrankNicolson"), i.e. from `default`: the
+        # coefficient of the Sp terms is the default entry's, the one of fvm::ddt(T) the entry of T -- only one and the same is accepted
+        if _scheme(d, "ddtSchemes") != ddt:
+            raise FoamCaseError("ddtSchemes: with CrankNicolson for T the `default` entry must be the same scheme and coefficient "
+                                "(thermoScheme.H:53-64 reads the coefficient from the default entry)")
+        if len(words) > 2:
+            raise FoamCaseError(f"ddtSchemes {ddt!r}: a constant off-centring coefficient is implemented, not a function of time")
+        oc_coeff = float(words[1]) if len(words) == 2 else 1.0       # [UPSTREAM] CrankNicolsonDdtScheme: psi = 1 when none is given
+        if not 0.0 <= oc_coeff <= 1.0:
+            raise FoamCaseError(f"ddtSchemes {ddt!r}: the off-centring coefficient must lie in [0, 1]")
+    ddt = words[0]
     # `laplacian(kappa,T)` is one word to OpenFOAM but a word plus a list to this module's grammar: look for it in the text itself
     text = re.sub(r"//[^\n]*|/\*.*?\*/", "", _read(case_dir, "system", "fvSchemes"), flags=re.S)
     m = re.search(r"laplacian\(\s*kappa\s*,\s*T\s*\)\s+([^;]+);", text)
@@ -390,7 +404,7 @@ def _check_schemes(case_dir):
     interp = _scheme(d, "interpolationSchemes")
     if interp != "linear":
         raise FoamCaseError(f"interpolationSchemes default {interp!r}: the diffusion-number kernel implements linear interpolation")
-    return abi.DDT_BACKWARD if ddt == "backward" else abi.DDT_EULER
+    return {"Euler": abi.DDT_EULER, "backward": abi.DDT_BACKWARD, "CrankNicolson": abi.DDT_CRANK_NICOLSON}[ddt], oc_coeff
 
 
 def _read_powder(case_dir, mesh):

@@ -49,7 +49,7 @@ enum { B200_SUPER_GAUSSIAN = 0, B200_MODIFIED_SUPER_GAUSSIAN = 1, B200_PROJECTED
 /* absorptionModel run-time types (MHS/absorptionModels/...). */
 enum { B200_ABSORPTION_CONSTANT = 0, B200_ABSORPTION_KELLY = 1 };
 enum { B200_KELLY_CONE = 0, B200_KELLY_CYLINDER = 1 };
-enum { B200_DDT_EULER = 0, B200_DDT_BACKWARD = 1 };
+enum { B200_DDT_EULER = 0, B200_DDT_BACKWARD = 1, B200_DDT_CRANK_NICOLSON = 2 };
 /* Fields that b200_case_get_field / set_field can address. */
 enum {
     B200_FIELD_T = 0, B200_FIELD_ALPHA_SOLID = 1, B200_FIELD_ALPHA_POWDER = 2,
@@ -60,6 +60,7 @@ enum {
     B200_FIELD_T_OLD = 8, B200_FIELD_ALPHA_SOLID_OLD = 9,
     /* the second old-time level (T.oldTime().oldTime(), ...), kept only with ddtScheme backward */
     B200_FIELD_T_OLD_OLD = 10, B200_FIELD_ALPHA_SOLID_OLD_OLD = 11,
+    B200_FIELD_DDT0_T = 12, B200_FIELD_DDT0_ALPHA_SOLID = 13,   /* CrankNicolson: the scheme's ddt0(T), ddt0(alpha.solid) */
     /* OR-ed into the field id of b200_case_set_field: upload only, leave the old-time copy and the patch state alone
      * (a host application that owns the field between steps re-uploads the same values) */
     B200_FIELD_KEEP_OLD = 0x100
@@ -131,8 +132,10 @@ typedef struct b200_controls {
     int32_t preconditioner;    /* B200_PRECOND_* */
     double  tolerance, relTol;
     int32_t minIter, maxIter;
-    int32_t ddtScheme;         /* system/fvSchemes ddtSchemes default: B200_DDT_EULER | B200_DDT_BACKWARD (SOLVER/thermo/thermoScheme.H:2-15,41-49);
-                                * CrankNicolson (:51-65) is not implemented and must be refused by the caller */
+    int32_t ddtScheme;         /* system/fvSchemes ddtSchemes default: B200_DDT_EULER | B200_DDT_BACKWARD | B200_DDT_CRANK_NICOLSON
+                                * (SOLVER/thermo/thermoScheme.H:2-15,41-65) */
+    double  ocCoeff;           /* CrankNicolson off-centring coefficient psi of `default CrankNicolson psi;` (0..1; 1 when the entry gives
+                                * none): [UPSTREAM] CrankNicolsonDdtScheme::ocCoeff(), read by thermoScheme.H:53-64.  Ignored otherwise. */
 } b200_controls;
 
 typedef struct b200_case_desc {

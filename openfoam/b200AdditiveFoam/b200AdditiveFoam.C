@@ -11,7 +11,7 @@
 
   What the resident step does not implement is refused up front instead of being approximated (the reference accepts more):
     * flow coupling: PIMPLE nOuterCorrectors > 0 (pU/UEqn.H, pU/pEqn.H, fvm::div(phi, T) with phi != 0)
-    * ddtSchemes CrankNicolson (thermoScheme.H:51-65; Euler and backward are implemented)
+    * ddtSchemes CrankNicolson with a time-dependent off-centring coefficient (a constant one is implemented, thermoScheme.H:51-65)
     * laplacian(kappa,T) other than Gauss harmonic, meshes that are not one uniform blockMesh hex block,
       patch types other than zeroGradient / fixedValue (uniform) / mixedTemperature, decompositions other than z-slabs
 
@@ -108,10 +108,21 @@ int main(int argc, char *argv[])
     {
         refuse("PIMPLE nOuterCorrectors > 0 (flow coupling)");
     }
-    const word ddtScheme(mesh.schemesDict().subDict("ddtSchemes").lookup("default"));      // thermoScheme.H:2 (no per-field entry in the tutorials)
-    if (ddtScheme != "Euler" && ddtScheme != "backward")
+    ITstream& ddtStream = mesh.schemesDict().subDict("ddtSchemes").lookup("default");      // thermoScheme.H:2 (no per-field entry in the tutorials)
+    const word ddtScheme(ddtStream);
+    scalar ocCoeff = 1;                                  // [UPSTREAM] CrankNicolsonDdtScheme: psi = 1 when the entry gives none
+    if (ddtScheme != "Euler" && ddtScheme != "backward" && ddtScheme != "CrankNicolson")
     {
-        refuse("ddtSchemes other than Euler and backward");
+        refuse("ddtSchemes other than Euler, backward and CrankNicolson");
+    }
+    if (ddtScheme == "CrankNicolson" && !ddtStream.eof())
+    {
+        token t(ddtStream);
+        if (!t.isNumber())
+        {
+            refuse("CrankNicolson with an off-centring coefficient that is a function of time");
+        }
+        ocCoeff = t.number();
     }
     {
         const dictionary& lap = mesh.schemesDict().subDict("laplacianSchemes");
@@ -287,7 +298,8 @@ int main(int argc, char *argv[])
         ct.minIter = sd.lookupOrDefault<label>("minIter", 0);
         ct.maxIter = sd.lookupOrDefault<label>("maxIter", 1000);
     }
-    ct.ddtScheme = ddtScheme == "backward" ? B200_DDT_BACKWARD : B200_DDT_EULER;
+    ct.ddtScheme = ddtScheme == "backward" ? B200_DDT_BACKWARD : ddtScheme == "CrankNicolson" ? B200_DDT_CRANK_NICOLSON : B200_DDT_EULER;
+    ct.ocCoeff = ocCoeff;
     desc.Tinitial = gAverage(T.primitiveField());       // overwritten below by the field itself
     desc.powderZMin = 1e300;                            // alpha.powder comes from the file, see below
 

@@ -208,6 +208,8 @@ static Field* fieldOf(RankState& s, int f)
     case B200_FIELD_ALPHA_SOLID_OLD: return &s.alpha1old;
     case B200_FIELD_T_OLD_OLD: return &s.Toldold;
     case B200_FIELD_ALPHA_SOLID_OLD_OLD: return &s.alpha1oldold;
+    case B200_FIELD_DDT0_T: return &s.ddt0T;
+    case B200_FIELD_DDT0_ALPHA_SOLID: return &s.ddt0A;
     }
     return nullptr;
 }
@@ -217,6 +219,7 @@ int afo_case_get_field(void* h, int f, scalar* out)
     for (auto& s : ((Case*)h)->rk) {
         Field* F = fieldOf(s, f);
         if (!F) return 1;
+        if (F->empty()) F->assign(s.mesh.nCells(), 0.0);          // ddt0 before the scheme's first use
         std::memcpy(out + off, F->data(), sizeof(scalar) * F->size());
         off += F->size();
     }
@@ -230,6 +233,7 @@ int afo_case_set_field(void* h, int f, const scalar* in)
         RankState& s = c->rk[r];
         Field* F = fieldOf(s, f);
         if (!F) return 1;
+        if (F->empty()) F->assign(s.mesh.nCells(), 0.0);
         std::memcpy(F->data(), in + off, sizeof(scalar) * F->size());
         off += F->size();
         if (f == B200_FIELD_T) { s.Told = s.T; c->correctTBoundary(r); }
@@ -338,6 +342,26 @@ int afo_case_time_scheme_state(void* h, scalar* deltaTSave, int* TnOld, int* a1n
 {
     Case* c = (Case*)h;
     *deltaTSave = c->deltaTSave; *TnOld = c->TnOld; *a1nOld = c->a1nOld;
+    return 0;
+}
+// CrankNicolson: the scheme's state as the last step's TEqn.H found it.  state[9] = timeIndex, TnOld, a1nOld, then for ddt0(T) and
+// ddt0(alpha.solid): exists, startTimeIndex, timeIndex.  The fields (zeros where ddt0 did not exist yet) go to ddt0T / ddt0A.
+int afo_case_cn_snapshot(void* h, int* state, scalar* ddt0T, scalar* ddt0A)
+{
+    Case* c = (Case*)h;
+    const Case::CnSnapshot& q = c->cnSnap;
+    const int st[9] = {(int)q.timeIndex, q.TnOld, q.a1nOld, q.T.exists, (int)q.T.startTimeIndex, (int)q.T.timeIndex,
+                       q.A.exists, (int)q.A.startTimeIndex, (int)q.A.timeIndex};
+    for (int i = 0; i < 9; i++) state[i] = st[i];
+    size_t off = 0;
+    for (int r = 0; r < c->R; r++) {
+        const size_t n = (size_t)c->rk[r].mesh.nCells();
+        for (size_t i = 0; i < n; i++) {
+            ddt0T[off + i] = r < (int)q.ddt0T.size() && q.ddt0T[r].size() == n ? q.ddt0T[r][i] : 0.0;
+            ddt0A[off + i] = r < (int)q.ddt0A.size() && q.ddt0A[r].size() == n ? q.ddt0A[r][i] : 0.0;
+        }
+        off += n;
+    }
     return 0;
 }
 scalar afo_mixed_value_fraction(scalar h, scalar emissivity, scalar Tinf, scalar Tp, scalar kap, scalar deltaCoeff)

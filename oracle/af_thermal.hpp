@@ -181,7 +181,8 @@ struct HeatSource {
 struct RankState {
     Mesh mesh;
     Field T, Told, alpha1, alpha1old, alpha3, kappa, Cp, qDot, dFdT, T0;
-    Field Toldold, alpha1oldold;        // second old-time level (ddtScheme backward)
+    Field Toldold, alpha1oldold;        // second old-time level (ddtScheme backward, CrankNicolson)
+    Field ddt0T, ddt0A;                 // [UPSTREAM] CrankNicolsonDdtScheme: ddt0(T), ddt0(alpha.solid)
     bool alpha1HasOld = false;
     // base TEqn, built once per step (thermoScheme.H)
     LduMatrix teqn;                     // diag, upper (implicit) + bouCoeffs for processor patches
@@ -218,6 +219,24 @@ struct Case {
         return k;
     }
     void touchOldTimes(bool ofT, int levels);
+    // [UPSTREAM] CrankNicolsonDdtScheme (finiteVolume/finiteVolume/ddtSchemes/CrankNicolsonDdtScheme), restated.  Per field the scheme
+    // keeps ddt0(name), created zero at its first use with startTimeIndex = the time index of that moment (DDt0Field, NO_READ form),
+    // and with GeometricField's own timeIndex set to the same.  With psi = ocCoeff():
+    //   coef_  = timeIndex > startTimeIndex ? 1 + psi : 1          rDtCoef_  = coef_/deltaT
+    //   coef0_ = timeIndex > startTimeIndex + 1 ? 1 + psi : 1      rDtCoef0_ = coef0_/deltaT0          (Time::deltaT0_, unguarded)
+    //   offCentre_(ddt0) = psi < 1 ? psi*ddt0 : ddt0
+    //   evaluate(ddt0) = ddt0.timeIndex() != timeIndex : ddt0 = rDtCoef0_*(vf.oldTime() - vf.oldTime().oldTime()) - offCentre_(ddt0)
+    //   fvcDdt = rDtCoef_*(vf - vf.oldTime()) - offCentre_(ddt0)
+    //   fvmDdt: diag = rDtCoef_*V, source = (rDtCoef_*vf.oldTime() + offCentre_(ddt0))*V   (vf.oldTime().oldTime() touched in any case)
+    //   and ddt0.timeIndex() = timeIndex at the end of either.
+    // ddt0 is AUTO_WRITE in the reference and read back at a restart; this restatement starts the history anew at a restart.
+    struct Ddt0State { bool exists = false; label startTimeIndex = 0, timeIndex = 0; };
+    Ddt0State ddt0StateT, ddt0StateA;
+    bool crankNicolson() const { return d.controls.ddtScheme == B200_DDT_CRANK_NICOLSON; }
+    scalar offCentre(scalar ddt0) const { return d.controls.ocCoeff < 1 ? d.controls.ocCoeff * ddt0 : ddt0; }
+    scalar cnPrepare(bool ofT, bool fvm);       // everything up to the use of ddt0; returns rDtCoef_
+    // test probe: the scheme's state as the last step's TEqn.H found it (right after runTime++), for tests/golden/make_ref_teqn_golden.py
+    struct CnSnapshot { Ddt0State T, A; int TnOld = 0, a1nOld = 0; label timeIndex = 0; Fields ddt0T, ddt0A; } cnSnap;
     label timeIndex = 0, writeTimeIndex = 0;
     scalar alphaCoNum = 0, DiNum = 0;
     bool verbose = false;
@@ -291,7 +310,7 @@ inline void Case::init(const b200_case_desc& desc, int nRanks)
         s.teqn.addr = &s.mesh.addr; s.teqn.interfaces = &s.mesh.interfaces;
     });
     time = d.controls.startTime; deltaT = d.controls.deltaT; deltaT0 = deltaT; deltaTSave = deltaT; timeIndex = 0; writeTimeIndex = 0;
-    TnOld = 0; a1nOld = 0;
+    TnOld = 0; a1nOld = 0; ddt0StateT = Ddt0State(); ddt0StateA = Ddt0State();
     sources.resize(d.nBeams);
     for (int b = 0; b < d.nBeams; b++) {
         const b200_beam& bs = d.beams[b];
@@ -412,6 +431,31 @@ inline void Case::touchOldTimes(bool ofT, int levels)
     n = std::max(n, levels);
 }
 
+inline scalar Case::cnPrepare(bool ofT, bool fvm)
+{
+    Ddt0State& st = ofT ? ddt0StateT : ddt0StateA;
+    if (!st.exists) {
+        forRanks(R, [&](int r) { (ofT ? rk[r].ddt0T : rk[r].ddt0A).assign(rk[r].mesh.nCells(), 0.0); });
+        st.exists = true; st.startTimeIndex = timeIndex; st.timeIndex = timeIndex;
+    }
+    const scalar psi = d.controls.ocCoeff;
+    const scalar rDtCoef = (timeIndex > st.startTimeIndex ? 1 + psi : 1) / deltaT;
+    touchOldTimes(ofT, fvm ? 2 : 1);
+    if (st.timeIndex != timeIndex) {
+        touchOldTimes(ofT, 2);
+        const scalar rDtCoef0 = (timeIndex > st.startTimeIndex + 1 ? 1 + psi : 1) / deltaT0;
+        forRanks(R, [&](int r) {
+            RankState& s = rk[r];
+            Field& d0 = ofT ? s.ddt0T : s.ddt0A;
+            const Field& o = ofT ? s.Told : s.alpha1old;
+            const Field& oo = ofT ? s.Toldold : s.alpha1oldold;
+            for (label c = 0; c < s.mesh.nCells(); c++) d0[c] = rDtCoef0 * (o[c] - oo[c]) - offCentre(d0[c]);
+        });
+    }
+    st.timeIndex = timeIndex;
+    return rDtCoef;
+}
+
 inline void Case::setDeltaT()
 {
     const b200_controls& ct = d.controls;
@@ -420,12 +464,15 @@ inline void Case::setDeltaT()
     const scalar rDeltaT = 1.0 / deltaT;
     // setDeltaT.H:6-11 fvc::ddt(T) with the scheme of fvSchemes: Euler rDeltaT*(T - T.oldTime()), or backward
     const BackwardCoeffs kb = backwardCoeffs(TnOld);
-    touchOldTimes(true, backward() ? 2 : 1);
+    const bool cn = crankNicolson();
+    const scalar rDtCoef = cn ? cnPrepare(true, false) : 0.0;
+    if (!cn) touchOldTimes(true, backward() ? 2 : 1);
     forRanks(R, [&](int r) {
         RankState& s = rk[r];
         scalar mx = -vGreat;
         for (label c = 0; c < s.mesh.nCells(); c++) {
-            const scalar ddtT = backward() ? kb.rDeltaT * (kb.coefft * s.T[c] - kb.coefft0 * s.Told[c] + kb.coefft00 * s.Toldold[c])
+            const scalar ddtT = cn ? rDtCoef * (s.T[c] - s.Told[c]) - offCentre(s.ddt0T[c])
+                              : backward() ? kb.rDeltaT * (kb.coefft * s.T[c] - kb.coefft0 * s.Told[c] + kb.coefft00 * s.Toldold[c])
                                            : rDeltaT * (s.T[c] - s.Told[c]);
             mx = std::max(mx, std::fabs(ddtT) / (Tliq - Tsol) * deltaT);
         }
@@ -567,7 +614,9 @@ inline void Case::assembleBase(bool explicitSolve)
     // thermoScheme.H:25-39: the explicit form always uses EulerDdtScheme; the implicit one fvm::ddt(T) with the scheme of fvSchemes
     const bool bwd = backward() && !explicitSolve;
     const BackwardCoeffs kT = backwardCoeffs(TnOld);
-    touchOldTimes(true, bwd ? 2 : 1);
+    const bool cn = crankNicolson() && !explicitSolve;
+    const scalar rDtCoef = cn ? cnPrepare(true, true) : 0.0;
+    if (!cn) touchOldTimes(true, bwd ? 2 : 1);
     forRanks(R, [&](int r) {
         RankState& s = rk[r];
         const Mesh& m = s.mesh;
@@ -576,7 +625,10 @@ inline void Case::assembleBase(bool explicitSolve)
         s.teqn.diag.resize(n); s.source.resize(n);
         for (label c = 0; c < n; c++) {
             const scalar rhoCp = rho * s.Cp[c];
-            if (bwd) {      // [UPSTREAM] backwardDdtScheme::fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*old - coefft00*oldOld)
+            if (cn) {       // [UPSTREAM] CrankNicolsonDdtScheme::fvmDdt: diag = rDtCoef*V, source = (rDtCoef*old + offCentre(ddt0))*V
+                s.teqn.diag[c] = (rDtCoef * m.V) * rhoCp;
+                s.source[c] = ((rDtCoef * s.Told[c] + offCentre(s.ddt0T[c])) * m.V) * rhoCp;
+            } else if (bwd) {      // [UPSTREAM] backwardDdtScheme::fvmDdt: diag = (coefft*rDeltaT)*V, source = rDeltaT*V*(coefft0*old - coefft00*oldOld)
                 s.teqn.diag[c] = ((kT.coefft * kT.rDeltaT) * m.V) * rhoCp;
                 s.source[c] = (kT.rDeltaT * m.V * (kT.coefft0 * s.Told[c] - kT.coefft00 * s.Toldold[c])) * rhoCp;
             } else {
@@ -698,7 +750,9 @@ inline SolverPerf Case::solveCorrector(bool explicitSolve, scalar rDeltaT, scala
     // TEqn.H:36-39: Euler fvcDdt(alpha1) when ddtScheme == "Euler" (always so in the explicit form, thermoScheme.H:22), else fvc::ddt
     const bool bwdA = backward() && !explicitSolve;
     const BackwardCoeffs kA = backwardCoeffs(a1nOld);
-    touchOldTimes(false, bwdA ? 2 : 1);
+    const bool cnA = crankNicolson() && !explicitSolve;
+    const scalar rDtCoefA = cnA ? cnPrepare(false, false) : 0.0;
+    if (!cnA) touchOldTimes(false, bwdA ? 2 : 1);
     const scalar Tmax = d.controls.Tmax > 0 ? d.controls.Tmax : vGreat;
     std::vector<LduMatrix> A(R);
     Fields totalSource(R), psi(R);
@@ -716,7 +770,8 @@ inline SolverPerf Case::solveCorrector(bool explicitSolve, scalar rDeltaT, scala
             const scalar source1 = (m.V * (Acoef * Tmax)) * rDeltaT;
             const scalar diag2 = (m.V * s.dFdT[c]) * s2;
             const scalar source2 = (m.V * (s.dFdT[c] * s.T0[c])) * s2;
-            const scalar su = bwdA ? (rho * Lf) * (kA.rDeltaT * (kA.coefft * s.alpha1[c] - kA.coefft0 * s.alpha1old[c] + kA.coefft00 * s.alpha1oldold[c]))
+            const scalar su = cnA ? (rho * Lf) * (rDtCoefA * (s.alpha1[c] - s.alpha1old[c]) - offCentre(s.ddt0A[c]))
+                            : bwdA ? (rho * Lf) * (kA.rDeltaT * (kA.coefft * s.alpha1[c] - kA.coefft0 * s.alpha1old[c] + kA.coefft00 * s.alpha1oldold[c]))
                                    : (rho * Lf) * (rDeltaTEuler * (s.alpha1[c] - s.alpha1old[c]));
             const scalar sourceR = source2 - m.V * su;
             M.diag[c] = (M.diag[c] + diag1) - diag2;
@@ -925,6 +980,11 @@ inline void Case::step(b200_step_report* rep)
     });
     deltaT0 = deltaTSave; deltaTSave = deltaT;          // [UPSTREAM] Time::operator++
     time += deltaT; timeIndex++;
+    if (crankNicolson()) {
+        cnSnap.T = ddt0StateT; cnSnap.A = ddt0StateA; cnSnap.TnOld = TnOld; cnSnap.a1nOld = a1nOld; cnSnap.timeIndex = timeIndex;
+        cnSnap.ddt0T.assign(R, Field()); cnSnap.ddt0A.assign(R, Field());
+        for (int r = 0; r < R; r++) { cnSnap.ddt0T[r] = rk[r].ddt0T; cnSnap.ddt0A[r] = rk[r].ddt0A; }
+    }
     if (ct.writeInterval > 0) {                         // [UPSTREAM] Time::operator++ write-time bookkeeping
         const label wi = label(((time - ct.startTime) + 0.5 * deltaT) / ct.writeInterval);
         if (wi > writeTimeIndex) writeTimeIndex = wi;
@@ -952,6 +1012,7 @@ inline void Case::step(b200_step_report* rep)
     // runTime.deltaT0() itself, not the scheme's guarded one -- in the implicit form only
     scalar rDeltaT = 1.0 / deltaT;
     if (backward() && !explicitSolve) rDeltaT *= 1.0 + deltaT / (deltaT + deltaT0);
+    if (crankNicolson() && !explicitSolve) rDeltaT *= 1.0 + ct.ocCoeff;      // thermoScheme.H:51-65: coefft = 1 + ocCoeff, at every step
     forRanks(R, [&](int r) { std::fill(rk[r].dFdT.begin(), rk[r].dFdT.end(), 0.0); rk[r].T0 = rk[r].T; });
     int nCorrDone = 0, iterSum = 0;
     scalar residual = 0;

@@ -8,7 +8,9 @@
 //        nThermo (x y)...
 //        nPatches { type nSides side... value h emissivity Tinf }...
 //        nOldT nOldAlpha
-//        fields: T, T.oldTime() [, T.oldTime().oldTime()], alpha1, [alpha1 old levels...], kappa, Cp, qDot   (nx*ny*nz each)
+//        psi timeIndex  existsT startT tiT  existsA startA tiA       (CrankNicolson: ocCoeff, the time index after runTime++, and for
+//                                                                    ddt0(T) / ddt0(alpha.solid): exists, startTimeIndex, timeIndex())
+//        fields: T, T.oldTime() [, T.oldTime().oldTime()], alpha1, [alpha1 old levels...], kappa, Cp, qDot, [ddt0(T)], [ddt0(alpha.solid)]
 //        per patch: Tb[nFaces]
 // -> "nSolves iters..." (one solve per corrector pass), then T and alpha1 (hex floats, one line each), then per patch Tb and valueFraction.
 // Built by oracle/Makefile into oracle/_ref/refTEqn when /root/reference is present.  TEST INFRASTRUCTURE ONLY: it produces
@@ -77,6 +79,8 @@ int main()
         mesh.patches.push_back(pa);
     }
     int nOldT, nOldA; std::cin >> nOldT >> nOldA;
+    int cnT[3], cnA[3];
+    std::cin >> mesh.schemes_.ocCoeff_ >> runTime.timeIndex_ >> cnT[0] >> cnT[1] >> cnT[2] >> cnA[0] >> cnA[1] >> cnA[2];
     auto readField = [&](volScalarField& f, const char* name) { f.mesh_ = &mesh; f.name_ = name; f.i_ = Internal(n, 0.0); for (label c = 0; c < n; c++) std::cin >> f.i_[c]; };
     volScalarField T, alpha1, kappa, Cp;
     movingHeatSourceModel sources;
@@ -85,6 +89,13 @@ int main()
     readField(alpha1, "alpha.solid");
     for (volScalarField* f = &alpha1; nOldA > 0; nOldA--) { f->old_ = std::make_shared<volScalarField>(); readField(*f->old_, "alpha.solid_0"); f = f->old_.get(); }
     readField(kappa, "kappa"); readField(Cp, "Cp"); readField(sources.qDot_, "qDot");
+    auto readDdt0 = [&](const char* name, const int (&st)[3]) {
+        if (!st[0]) return;
+        DDt0Field& f = mesh.ddt0s[name];
+        f.i_.assign(n, 0.0); f.startTimeIndex_ = st[1]; f.timeIndex_ = st[2];
+        for (label c = 0; c < n; c++) std::cin >> f.i_[c];
+    };
+    readDdt0("ddt0(T)", cnT); readDdt0("ddt0(alpha.solid)", cnA);
     std::vector<TPatchState> tp(nPatches);
     for (int p = 0; p < nPatches; p++) {
         const size_t nf = mesh.patches[p].faceCells.size();

@@ -45,13 +45,25 @@ def configs():
     out["track_backward_tmax"] = (c, 40)
     c = cases.multi_layer_pbf(n=(32, 16, 10), nHatch=2, writeInterval=0.0, deltaT=1e-6, ddtScheme=abi.DDT_BACKWARD)
     out["pbf_backward"] = (c, 30)
+    # ddtSchemes default CrankNicolson psi (thermoScheme.H:51-65): the scheme's ddt0 fields, coefft = 1 + ocCoeff on the Sp terms
+    c = cases.amb2018_02_b(n=(40, 10, 6), writeInterval=0.0, explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC,
+                           ddtScheme=abi.DDT_CRANK_NICOLSON, ocCoeff=0.9)
+    out["amb_cn09_pcg"] = (c, 25)
+    c = cases.synthetic_track((36, 12, 8), writeInterval=0.0, deltaT=2e-6, Tmax=2500.0, nThermoCorrectors=6, thermoTolerance=1e-6,
+                              explicitSolve=0, maxDi=20.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC, ddtScheme=abi.DDT_CRANK_NICOLSON,
+                              ocCoeff=1.0)
+    out["track_cn1_tmax"] = (c, 40)
+    c = cases.multi_layer_pbf(n=(32, 16, 10), nHatch=2, writeInterval=0.0, deltaT=1e-6, ddtScheme=abi.DDT_CRANK_NICOLSON, ocCoeff=0.5)
+    out["pbf_cn05"] = (c, 30)
+    c = cases.amb2018_02_b(n=(40, 10, 6), writeInterval=0.0, ddtScheme=abi.DDT_CRANK_NICOLSON, ocCoeff=0.9)   # as shipped: explicit steps are Euler, ddt0(T) lives on in setDeltaT.H
+    out["amb_cn09_as_shipped_explicit"] = (c, 30)
     for case, _ in out.values():
         for b in case["beams"]:
             b["hitPathIntervals"] = 0
     return out
 
 
-def request(case, ddt, explicit, dt, dt0, Tliq, Tsol, nThermoCorr, T, Told_levels, alpha1, alpha_old_levels, kappa, Cp, qDot, patchTb):
+def request(case, ddt, explicit, dt, dt0, Tliq, Tsol, nThermoCorr, T, Told_levels, alpha1, alpha_old_levels, kappa, Cp, qDot, patchTb, cn=None):
     m, ct, mat = case["mesh"], case["controls"], case["material"]
     n = m["n"]
     d = [(m["max"][q] - m["min"][q]) / n[q] for q in range(3)]
@@ -64,7 +76,14 @@ def request(case, ddt, explicit, dt, dt0, Tliq, Tsol, nThermoCorr, T, Told_level
     for p in case["patches"]:
         lines.append("%d %d %s %r %r %r %r" % (p["type"], len(p["sides"]), " ".join(str(s) for s in p["sides"]), p["value"], p["h"], p["emissivity"], p["Tinf"]))
     lines.append("%d %d" % (len(Told_levels), len(alpha_old_levels)))
-    for f in [T, *Told_levels, alpha1, *alpha_old_levels, kappa, Cp, qDot, *patchTb]:
+    ddt0 = []
+    if cn is None:
+        lines.append("1.0 0  0 0 0  0 0 0")
+    else:
+        st = cn["state"]
+        lines.append("%r %d  %d %d %d  %d %d %d" % (ct["ocCoeff"], st["timeIndex"], st["existsT"], st["startT"], st["tiT"], st["existsA"], st["startA"], st["tiA"]))
+        ddt0 = ([cn["ddt0T"]] if st["existsT"] else []) + ([cn["ddt0A"]] if st["existsA"] else [])
+    for f in [T, *Told_levels, alpha1, *alpha_old_levels, kappa, Cp, qDot, *ddt0, *patchTb]:
         lines.append(" ".join(repr(float(v)) for v in f))
     return "\n".join(lines) + "\n"
 
@@ -108,8 +127,19 @@ def step_inputs(o, case, abi):
         T_levels = [T, o.field(abi.FIELD_T_OLD)]
         assert a1nOld in (0, 2)
         A_levels = [] if a1nOld == 0 else [A, o.field(abi.FIELD_ALPHA_SOLID_OLD)]
-    return dict(T=T, alpha1=A, T_levels=T_levels, A_levels=A_levels, deltaT0=dt_save, ddt="backward" if backward else "Euler",
-                patches=[tb.copy() for tb, _ in o.patch_state()])
+    cn = case["controls"]["ddtScheme"] == abi.DDT_CRANK_NICOLSON
+    return dict(T=T, alpha1=A, T_levels=T_levels, A_levels=A_levels, deltaT0=dt_save,
+                ddt="backward" if backward else "CrankNicolson" if cn else "Euler",
+                Told=o.field(abi.FIELD_T_OLD), Aold=o.field(abi.FIELD_ALPHA_SOLID_OLD), patches=[tb.copy() for tb, _ in o.patch_state()])
+
+
+def cn_inputs(o, pre):
+    """CrankNicolson, AFTER the step: the scheme's state as that step's TEqn.H found it (setDeltaT.H has already used ddt0(T) at the
+    previous time index; runTime++ has shifted the old-time levels that existed) and the old-time levels of T and alpha.solid it saw."""
+    st, d0T, d0A = o.cn_snapshot()
+    pre["T_levels"] = [pre["T"]] + ([pre["Told"]] if st["TnOld"] >= 2 else [])
+    pre["A_levels"] = [] if st["a1nOld"] == 0 else [pre["alpha1"]] + ([pre["Aold"]] if st["a1nOld"] >= 2 else [])
+    return dict(state=st, ddt0T=d0T, ddt0A=d0A)
 
 
 def main():
@@ -127,9 +157,10 @@ def main():
             rep = o.step()
             kappa, Cp, qDot = (o.field(f) for f in (abi.FIELD_KAPPA, abi.FIELD_CP, abi.FIELD_QDOT))
             # after runTime++ the old-time level of T and alpha.solid is the start-of-step field
+            cn = cn_inputs(o, pre) if pre["ddt"] == "CrankNicolson" else None
             req = request(case, pre["ddt"], rep.explicitStep, rep.deltaT, pre["deltaT0"], o.L.afo_case_Tliq(o.h), o.L.afo_case_Tsol(o.h),
                           case["controls"]["nThermoCorrectors"] if (rep.totalPower > 1e-15 or pre["alpha1"].min() < 1 - 1e-15) else 1,
-                          pre["T"], pre["T_levels"], pre["alpha1"], pre["A_levels"], kappa, Cp, qDot, pre["patches"])
+                          pre["T"], pre["T_levels"], pre["alpha1"], pre["A_levels"], kappa, Cp, qDot, pre["patches"], cn)
             its, T, A, Tb, vf = parse(run_ref(req), len(case["patches"]))
             To, Ao = o.field(abi.FIELD_T), o.field(abi.FIELD_ALPHA_SOLID)
             worst = max(worst, float(np.max(np.abs(T - To)) / np.max(np.abs(To))), float(np.max(np.abs(A - Ao))))

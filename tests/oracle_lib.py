@@ -43,6 +43,7 @@ def load():
     L.afo_case_pre_step_state.argtypes = [C.c_void_p, dp]
     L.afo_case_reset_alpha_solid.argtypes = [C.c_void_p]
     L.afo_case_time_scheme_state.argtypes = [C.c_void_p, dp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.afo_case_cn_snapshot.argtypes = [C.c_void_p, C.POINTER(C.c_int), dp, dp]
     L.afo_case_n_patches.argtypes = [C.c_void_p]
     L.afo_case_patch_size.restype = C.c_int64
     L.afo_case_patch_size.argtypes = [C.c_void_p, C.c_int]
@@ -124,6 +125,14 @@ class OracleCase:
         dts, a, b = C.c_double(0.0), C.c_int(0), C.c_int(0)
         self.L.afo_case_time_scheme_state(self.h, C.byref(dts), C.byref(a), C.byref(b))
         return dts.value, a.value, b.value
+
+    def cn_snapshot(self):
+        """CrankNicolson: (state dict, ddt0(T), ddt0(alpha.solid)) as the last step's TEqn.H found them, right after runTime++."""
+        st = (C.c_int * 9)()
+        dT, dA = np.zeros(self.n), np.zeros(self.n)
+        assert self.L.afo_case_cn_snapshot(self.h, st, P(dT), P(dA)) == 0
+        keys = ("timeIndex", "TnOld", "a1nOld", "existsT", "startT", "tiT", "existsA", "startA", "tiA")
+        return dict(zip(keys, [int(v) for v in st])), dT, dA
 
     def pre_step_state(self):
         """updateProperties() (so that kappa, Cp are what the next step's controls see) and T.oldTime()."""

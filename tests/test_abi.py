@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in declared if not hasattr(L, s)]
     assert not missing, missing
     assert sorted(lib.SYMBOLS) == declared          # the python binding names exactly the header's surface
-    assert L.b200_abi_version() == 2          # 2: b200_controls.ddtScheme
+    assert L.b200_abi_version() == 3          # 2: b200_controls.ddtScheme; 3: ocCoeff (CrankNicolson)
 
 
 def test_struct_sizes_match_header_layout():

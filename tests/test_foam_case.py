@@ -177,7 +177,9 @@ def test_what_cannot_be_represented_is_refused(tmp_path):
 
 @pytest.mark.parametrize("rel,old,new,match", [
     ("system/fvSolution", "nOuterCorrectors 0;", "nOuterCorrectors 1;", "nOuterCorrectors"),
-    ("system/fvSchemes", "default Euler;", "default CrankNicolson 0.9;", "ddtSchemes"),
+    ("system/fvSchemes", "default Euler;", "default localEuler;", "ddtSchemes"),
+    ("system/fvSchemes", "default Euler;", "default CrankNicolson 1.2;", "ddtSchemes"),
+    ("system/fvSchemes", "default Euler;", "default Euler; T CrankNicolson 0.9;", "default"),      # thermoScheme.H:53-64 reads psi from `default`
     ("system/fvSchemes", "laplacian(kappa,T) Gauss harmonic corrected;", "", "laplacian"),
     ("system/fvSchemes", "interpolationSchemes { default linear; }", "interpolationSchemes { default cubic; }", "interpolationSchemes"),
 ])
@@ -342,6 +344,18 @@ def test_gpu_restart_from_a_written_time_directory(ctx, oracle, tmp_path):
         eA = float(np.max(np.abs(g2.field(abi.FIELD_ALPHA_SOLID) - o2.field(abi.FIELD_ALPHA_SOLID))))
         assert eT < 1e-9 and eA < 1e-9, (s, eT, eA)
     g2.close(); o2.close()
+
+
+def test_crank_nicolson_ddt_scheme_and_its_coefficient_are_read(tmp_path):
+    """ddtSchemes default CrankNicolson psi (thermoScheme.H:51-65): the scheme and its off-centring coefficient; none given means 1
+    ([UPSTREAM] CrankNicolsonDdtScheme)."""
+    for entry, psi in (("default CrankNicolson 0.9;", 0.9), ("default CrankNicolson;", 1.0), ("default CrankNicolson 0;", 0.0)):
+        root = write_case(tmp_path / ("cn%g" % psi))
+        path = os.path.join(root, "system", "fvSchemes")
+        text = open(path).read()
+        open(path, "w").write(text.replace("default Euler;", entry))
+        ctl = foamcase.read_case(root)["controls"]
+        assert ctl["ddtScheme"] == abi.DDT_CRANK_NICOLSON and ctl["ocCoeff"] == psi
 
 
 def test_backward_ddt_scheme_is_read(tmp_path):

@@ -77,13 +77,17 @@ def random_case(seed):
                 Tinitial=t_init, powderZMin=float(rng.choice([1e300, -0.4 * lz])))
 
 
-@pytest.mark.parametrize("seed", list(range(24)) + [100 + s for s in range(10)])
+@pytest.mark.parametrize("seed", list(range(24)) + [100 + s for s in range(10)] + [200 + s for s in range(12)])
 def test_random_case_matches_oracle(ctx, oracle, seed):
-    """Seeds >= 100: the same generator with ddtSchemes backward (thermoScheme.H:41-49) -- second old-time levels, the scheme's fvc::ddt
-    in setDeltaT.H and TEqn.H, explicit steps (always Euler) mixed in where the case asks for explicitSolve."""
+    """Seeds 100..: the same generator with ddtSchemes backward (thermoScheme.H:41-49) -- second old-time levels, the scheme's fvc::ddt
+    in setDeltaT.H and TEqn.H, explicit steps (always Euler) mixed in where the case asks for explicitSolve.  Seeds 200..: CrankNicolson
+    (thermoScheme.H:51-65) with off-centring coefficients 1, 0.9, 0.5 and 0 -- the scheme's ddt0 fields of T and alpha.solid."""
     case = random_case(seed % 100)
-    if seed >= 100:
+    if 100 <= seed < 200:
         case["controls"]["ddtScheme"] = abi.DDT_BACKWARD
+    if seed >= 200:
+        case["controls"]["ddtScheme"] = abi.DDT_CRANK_NICOLSON
+        case["controls"]["ocCoeff"] = (1.0, 0.9, 0.5, 0.0)[seed % 4]
     g, o = lib.Case(ctx, case), ol.OracleCase(case, lib=oracle)
     for s in range(25):
         rg, ro = g.step(), o.step()
@@ -94,4 +98,8 @@ def test_random_case_matches_oracle(ctx, oracle, seed):
         eT = helpers.rel_linf(g.field(abi.FIELD_T), o.field(abi.FIELD_T))
         eA = float(np.max(np.abs(g.field(abi.FIELD_ALPHA_SOLID) - o.field(abi.FIELD_ALPHA_SOLID))))
         assert eT < 1e-9 and eA < 1e-9, f"seed {seed} step {s}: T {eT:.3e} alpha {eA:.3e}"
+    if seed >= 200:
+        for f in (abi.FIELD_DDT0_T, abi.FIELD_DDT0_ALPHA_SOLID):
+            dg, do = g.field(f), o.field(f)
+            assert np.max(np.abs(dg - do)) <= 1e-7 * max(np.max(np.abs(do)), 1e-300), f"seed {seed}: ddt0 field {f}"
     g.close(); o.close()

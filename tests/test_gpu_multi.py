@@ -15,7 +15,7 @@ def _ngpus():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("mode", ["implicit", "explicit", "bicg"])
+@pytest.mark.parametrize("mode", ["implicit", "explicit", "bicg", "backward", "cn"])
 def test_two_rank_parity(mode):
     if _ngpus() < 2:
         pytest.skip("needs 2 GPUs")

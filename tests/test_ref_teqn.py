@@ -2,7 +2,7 @@
 values computed by the REFERENCE's own text (tests/golden/ref_teqn.json, made by tests/golden/make_ref_teqn_golden.py from
 oracle/_ref/refTEqn = the three fragments included verbatim where they lie against an fvScalarMatrix stand-in).  The fragment was fed
 the oracle's state at the start of every step of five small cases (as-shipped explicit; implicit PCG/DIC; implicit with the as-shipped
-PBiCGStab/DILU; the Tmax penalty active; powder layer with fixedValue walls; and three of them again with ddtSchemes backward, where
+PBiCGStab/DILU; the Tmax penalty active; powder layer with fixedValue walls; three of them again with ddtSchemes backward and again with CrankNicolson (psi 0.9, 1, 0.5), where
 thermoScheme.H scales the rDeltaT of the Sp terms by coefft and TEqn.H takes fvc::ddt(alpha1) from the scheme), so re-running the cases must give, step by step, the
 reference text's T, alpha.solid, face values and value fractions of every patch, and the Krylov iterations of every corrector pass.
 Checked: the oracle (CPU, bit for bit) and the GPU stepper through b200_case_step (1e-9; iterations +-1).
@@ -76,6 +76,11 @@ def test_fixture_covers_the_branches_of_the_equation():
     # first step is where alpha.solid has no old-time level yet
     assert GOLD["amb_backward_pcg"][0]["T"]["sum"] != GOLD["amb_implicit_pcg"][0]["T"]["sum"]
     assert GOLD["track_backward_tmax"][-1]["T"]["val"] != GOLD["track_tmax"][-1]["T"]["val"]
+    # the CrankNicolson cases: different from Euler and from backward; the as-shipped one takes explicit (Euler) steps while ddt0(T)
+    # lives on in setDeltaT.H
+    assert GOLD["amb_cn09_pcg"][-1]["T"]["sum"] not in (GOLD["amb_implicit_pcg"][-1]["T"]["sum"], GOLD["amb_backward_pcg"][-1]["T"]["sum"])
+    assert GOLD["pbf_cn05"][-1]["T"]["val"] != GOLD["pbf"][-1]["T"]["val"]
+    assert all(it == 0 for r in GOLD["amb_cn09_as_shipped_explicit"] for it in r["iters"])
     assert max(H(v) for r in GOLD["track_tmax"] for v in r["T"]["val"]) > 1620.0 and max(H(v) for r in GOLD["amb_explicit"] for v in r["T"]["val"]) > 1410.0   # melting / mushy zone
 
 

@@ -1,5 +1,5 @@
 """Decomposed GPU run (one z-slab per rank, torchrun) checked against the CPU oracle's in-process emulation of the same
-ranks.  Usage: torchrun --nproc-per-node N tools/run_multi.py [implicit|explicit] [steps]"""
+ranks.  Usage: torchrun --nproc-per-node N tools/run_multi.py [implicit|explicit|bicg|backward|cn|funcobj|fuzz] [steps]"""
 import os
 import sys
 
@@ -110,6 +110,9 @@ n = (48, 14, 11)
 kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC) if mode == "implicit" else dict()
 if mode == "bicg":
     kw = dict(explicitSolve=0, maxDi=10.0)
+if mode in ("backward", "cn"):      # the other two ddt schemes of thermoScheme.H:4-15, decomposed
+    kw = dict(explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC,
+              ddtScheme=abi.DDT_BACKWARD if mode == "backward" else abi.DDT_CRANK_NICOLSON, ocCoeff=0.9)
 SOLID_ISO, ISO = 1500.0, [1620.0, 1410.0, 600.0]
 if mode == "funcobj":      # two z layers: every cell touches the slab interface, so the function objects cross processor faces
     n, SOLID_ISO, ISO = (48, 14, 2), 600.0, [900.0, 600.0, 400.0]
