@@ -22,6 +22,7 @@ timeout 300 $B > gpurun_out/${TAG}_plain100.json 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches_100000000.csv $B > gpurun_out/${TAG}_ncu_list100.log 2>&1; lap "launch list 100 M"
 full ${TAG}_full_100000000 300 44 "$K"
 full ${TAG}_full_step_100000000 8 12 "$K2"
+[ "${THIN:-1}" = "0" ] && { du -sh gpurun_out | tail -1; exit 0; }      # THIN=0: the 100 M-cell part only
 timeout 200 $B --nz 32 > gpurun_out/${TAG}_plain12.json 2>&1 && \
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/${TAG}_launches_12800000.csv $B --nz 32 > gpurun_out/${TAG}_ncu_list12.log 2>&1; lap "launch list 12.8 M"
 full ${TAG}_full_12800000 300 44 "$K" --nz 32
