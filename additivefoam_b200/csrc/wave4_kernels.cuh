@@ -216,14 +216,13 @@ __global__ void __launch_bounds__(96, (RNG <= 3 ? 4 : RNG <= 4 ? 3 : 2)) k_wave4
         const bool wantY = lane < NEY && jY < g.ny && kY < g.nz && (bwd ? jY < g.ny - 1 : jY > 0);
         const int skewY = tjE + tkY;
         const double* XYp = X + ((size_t)(wantY ? upJ : T) * g.nStepsPad + (wantY ? dtY : 0)) * 32 + (bwd ? WTJ * tkY : WTJ - 1 + WTJ * tkY);
-        const int smY = sY * 32 + tjE + WTJ * tkY;
         // z-edge elements: e = lane + 32 r -> step e / WTJ, consumer lane (tjZ, tkE)
         const int tjZ = lane % WTJ, tkE = bwd ? WTK - 1 : 0;
         const int jZ = J * WTJ + tjZ, kZ = K * WTK + tkE;
         const bool wantZ = jZ < g.ny && kZ < g.nz && (bwd ? kZ < g.nz - 1 : kZ > 0);
         const int skewZ = tjZ + tkE;
         const double* XZp = X + ((size_t)(wantZ ? upK : T) * g.nStepsPad + (wantZ ? dtZ : 0)) * 32 + (bwd ? tjZ : tjZ + WTJ * (WTK - 1));
-        const int sZ0 = lane / WTJ, smZ = tjZ + WTJ * tkE;
+        const int sZ0 = lane / WTJ;
         double vY[DEPTH], vZ[DEPTH][NZ];
         auto first = [&](int grp, double& y, double (&z)[NZ]) {
             const int tb = tbOf(grp);
