@@ -74,3 +74,17 @@ def test_gpu_two_layers_against_the_oracle(ctx, oracle):
     T2, P2, t2, power = check_layer(new, T1, P1, 60)
     assert t2 > t_end and power > 0.0                    # the beam is on again in the second layer: its path waited for the start time
     assert T2.size == T.size + 2 * 80 * 16
+
+
+@pytest.mark.gpu
+def test_gpu_run_layers_driver(ctx):
+    """layers.run_layers: the loop of runLayers:152-205 -- every layer to its end time on the device, the callback once per layer."""
+    case = _case(n=(80, 16, 8), cell=20e-6)
+    seen = []
+    last, T, P = layers.run_layers(ctx, case, 3, 40e-6, 2, on_layer_end=lambda layer, c, T_, P_: seen.append((layer, c["mesh"]["n"][2], T_.size, float(T_.max()))))
+    assert [s[:3] for s in seen] == [(0, 8, 80 * 16 * 8), (1, 10, 80 * 16 * 10), (2, 12, 80 * 16 * 12)]
+    assert all(s[3] > 1000.0 for s in seen)                                        # the beam came on in every layer
+    assert last["mesh"]["n"][2] == 12 and np.isclose(last["controls"]["startTime"], 4e-5) and np.isclose(last["controls"]["endTime"], 6e-5)
+    assert last["beams"][0]["path"][0][5] == last["controls"]["startTime"]
+    assert T.size == P.size == 80 * 16 * 12
+    assert P.reshape(12, 16, 80)[:8].max() <= 1.0 and P.reshape(12, 16, 80)[10:].max() == 1.0      # powder left beside the tracks of the last layer
