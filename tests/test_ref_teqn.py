@@ -96,3 +96,41 @@ def test_gpu_equation_matches_the_reference_text(ctx, name):
         close(g.field(abi.FIELD_T), want["T"], f"T, step {s}", 1e-9)
         close(g.field(abi.FIELD_ALPHA_SOLID), want["alpha1"], f"alpha.solid, step {s}", 1e-9, scale=1.0)
     g.close()
+
+
+def test_crank_nicolson_with_zero_off_centring_is_euler(oracle):
+    """psi = 0 switches every off-centre term off and leaves coef_ = 1: the run must be the Euler run bit for bit, while the scheme's
+    bookkeeping (ddt0 fields, second old-time levels) runs all the same.  With psi > 0 the first TEqn.H already uses coef_ = 1 + psi,
+    because setDeltaT.H created ddt0(T) one time index earlier; ddt0(alpha.solid) is created inside the first corrector loop."""
+    kw = dict(n=(40, 10, 6), writeInterval=0.0, explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC)
+    from additivefoam_b200 import cases
+    e = ol.OracleCase(cases.amb2018_02_b(**kw), lib=oracle)
+    z = ol.OracleCase(cases.amb2018_02_b(ddtScheme=abi.DDT_CRANK_NICOLSON, ocCoeff=0.0, **kw), lib=oracle)
+    c = ol.OracleCase(cases.amb2018_02_b(ddtScheme=abi.DDT_CRANK_NICOLSON, ocCoeff=0.9, **kw), lib=oracle)
+    for s in range(20):
+        re_, rz, rc = e.step(), z.step(), c.step()
+        assert np.array_equal(e.field(abi.FIELD_T), z.field(abi.FIELD_T)) and rz.deltaT == re_.deltaT, s
+        assert np.array_equal(e.field(abi.FIELD_ALPHA_SOLID), z.field(abi.FIELD_ALPHA_SOLID)), s
+        st = c.cn_snapshot()[0]
+        assert st["timeIndex"] == s + 1 and st["existsT"] == 1 and st["startT"] == 0 and st["tiT"] == s      # brought to index s by setDeltaT.H
+        assert (st["existsA"], st["startA"]) == ((0, 0) if s == 0 else (1, 1))
+        assert st["TnOld"] == (1 if s == 0 else 2)
+    assert not np.array_equal(c.field(abi.FIELD_T), e.field(abi.FIELD_T))
+    assert np.abs(z.field(abi.FIELD_DDT0_T)).max() > 0.0          # ddt0 = (T.old - T.oldOld)/deltaT0 is kept even though psi = 0 never uses it
+
+
+@pytest.mark.gpu
+def test_gpu_crank_nicolson_with_zero_off_centring_is_euler(ctx):
+    """The same identity on the device: CnCoeffs with psi = 0 takes the CrankNicolson branches of k_props, k_assemble_implicit and
+    k_corrector and must reproduce the Euler branches bit for bit."""
+    from additivefoam_b200 import cases
+    kw = dict(n=(60, 12, 8), writeInterval=0.0, explicitSolve=0, maxDi=10.0, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC)
+    e = lib.Case(ctx, cases.amb2018_02_b(**kw))
+    z = lib.Case(ctx, cases.amb2018_02_b(ddtScheme=abi.DDT_CRANK_NICOLSON, ocCoeff=0.0, **kw))
+    for s in range(30):
+        re_, rz = e.step(), z.step()
+        assert rz.deltaT == re_.deltaT and rz.lastSolveIterations == re_.lastSolveIterations, s
+    assert np.array_equal(e.field(abi.FIELD_T), z.field(abi.FIELD_T)) and e.field(abi.FIELD_T).max() > 1000.0
+    assert np.array_equal(e.field(abi.FIELD_ALPHA_SOLID), z.field(abi.FIELD_ALPHA_SOLID))
+    assert np.abs(z.field(abi.FIELD_DDT0_T)).max() > 0.0
+    e.close(); z.close()
