@@ -442,8 +442,10 @@ void Ldu::waveSweep(int op, bool dilu, bool dot, const double* rA, double* wA, b
     const int forced = [] { const char* e = std::getenv("B200_WAVE"); return !e ? 0 : std::string(e) == "1warp" ? 1 : std::string(e) == "multi" ? 3 : std::string(e) == "tri" ? 4 : 2; }();
     const bool oneWarp = forced == 1;
     // default: where the dependency chain across tiles bounds the sweep (few tiles: thin slabs, small blocks) the three-role kernel
-    // k_wave4, whose tiles follow their producers at a third less lag; where bandwidth does (thousands of tiles) k_wave2
-    const bool tri = forced == 4 || (forced == 0 && a.g.nTiles <= 1536);
+    // k_wave4, whose tiles follow their producers at a third less lag; where bandwidth does k_wave2.  Measured inside a PCG/DIC solve
+    // (tools/perf_mid.sh, profiles/r2_mid_slab_sweeps.txt): 400 tiles (1000 x 400 x 31) 0.30 / 0.32 ms against 0.40 / 0.43; 800 tiles
+    // (1000 x 400 x 63) 0.40 / 0.49 against 0.41 / 0.42 and the factor sweep 1.22 against 1.09 ms; 1600 and more: k_wave2.
+    const bool tri = forced == 4 || (forced == 0 && a.g.nTiles <= 600);
     const bool multi = forced == 3;
     if (op == 0 && !oneWarp) {      // the warp-specialised factor sweep streams the diagonal from wave order as well
         k_wave_from_natural<<<waveVecGrid(), 256, 0, s>>>(a.g, rA, wave[13], 1.0, d_state); B200_LAUNCH_CHECK();

@@ -1,12 +1,13 @@
 """Oracle parity of the sweep-kernel instantiations that the benchmark actually runs.
 
-`Ldu::waveSweep` picks the kernel by tile count and environment: the many-tile schedule only when the block has more than
-1536 tiles of 8x4 pencils -- more than any other test reaches.  Here:
+`Ldu::waveSweep` picks the kernel by tile count and environment: the three-role k_wave4 up to 600 tiles of 8x4 pencils, k_wave2 with
+deep ring slots up to 1536, the many-tile schedule (k_wave2, ring 8 x 3) above that -- more than any other test reaches.  Here:
 
 * a 64x400x124 block (1550 tiles, 3.2 M cells): factor + forward + backward sweep `array_equal` with the oracle's face loops
   ([UPSTREAM] DICPreconditioner / DILUPreconditioner::calcReciprocalD + precondition) and a PCG/DIC solve
   with the as-shipped controls (fvSolution:38-41) at the north-star tolerance -- this is the default schedule of the 100 M-cell
   benchmark (ticket order over thousands of tiles, ring reuse, sentinel re-arming at scale);
+* a 64x400x60 block (750 tiles): the default between the two regimes;
 * every selectable schedule -- `B200_WAVE=single` (k_wave2, one tile per CTA) with each ring geometry `B200_WAVE2_RING`,
   `B200_WAVE=multi` (k_wave3, several tiles per CTA exchanging edges through shared memory) with each `B200_WAVE3` geometry,
   `B200_WAVE=1warp` -- on small and ragged blocks (one tile, partial tiles, fewer tiles in J than a CTA holds, ...);
@@ -66,6 +67,24 @@ def test_many_tile_schedule_sweeps_bit_exact(ctx, oracle, precond):
     ref = oracle_precond(oracle, n, lo, up, diag, upper, lower, precond, b)
     s.close()
     assert np.array_equal(got[0], ref) and np.array_equal(got[1], ref)
+
+
+MID = (64, 400, 60)           # 50 x 15 = 750 tiles: between the thin-slab regime (k_wave4 up to 600 tiles) and the many-tile one: k_wave2, ring 8 x 6
+
+
+@pytest.mark.parametrize("precond", [abi.PRECOND_DIC, abi.PRECOND_DILU])
+def test_mid_tile_count_default_schedule_bit_exact(ctx, oracle, precond):
+    """What a GPU gets of the 100 M-cell case on four GPUs (800 tiles) takes this default: factor + sweeps bit for bit, and a solve."""
+    asym = precond == abi.PRECOND_DILU
+    n, lo, up, diag, upper, lower, x0, b = big_block(oracle, MID, 41, asym)
+    s = lib.LduSolver(ctx, lo, up, n, block=MID)
+    got = s.precondition(precond, b, diag, upper, lower)
+    assert np.array_equal(got, oracle_precond(oracle, n, lo, up, diag, upper, lower, precond, b))
+    if not asym:
+        got, perf = s.solve(x0, b, diag, upper, None, solver=abi.SOLVER_PCG, preconditioner=abi.PRECOND_DIC, tolerance=1e-15, relTol=0.0, minIter=1, maxIter=20)
+        ref, rperf, _ = oracle_solve(oracle, n, lo, up, diag, upper, None, b, x0, abi.SOLVER_PCG, abi.PRECOND_DIC, 1e-15, 0.0, 1, 20)
+        assert perf.nIterations == rperf.nIterations and helpers.rel_linf(got, ref) < 1e-9
+    s.close()
 
 
 def test_many_tile_schedule_pcg_dic_solve(ctx, oracle):
