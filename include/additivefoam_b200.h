@@ -58,7 +58,7 @@ enum {
     /* old-time copies (T.oldTime(), alpha.solid.oldTime(); [UPSTREAM] GeometricField::storeOldTimes at runTime++,
      * additiveFoam.C:76): plain upload / download, for restarts and for resynchronising a run with another one */
     B200_FIELD_T_OLD = 8, B200_FIELD_ALPHA_SOLID_OLD = 9,
-    /* the second old-time level (T.oldTime().oldTime(), ...), kept only with ddtScheme backward */
+    /* the second old-time level (T.oldTime().oldTime(), ...), kept only with ddtScheme backward or CrankNicolson */
     B200_FIELD_T_OLD_OLD = 10, B200_FIELD_ALPHA_SOLID_OLD_OLD = 11,
     B200_FIELD_DDT0_T = 12, B200_FIELD_DDT0_ALPHA_SOLID = 13,   /* CrankNicolson: the scheme's ddt0(T), ddt0(alpha.solid) */
     /* OR-ed into the field id of b200_case_set_field: upload only, leave the old-time copy and the patch state alone
